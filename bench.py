@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the hot path (BASELINE.json metric M1):
+combined-GP NLL evaluations/sec, batched, n=100, 2-D anisotropic, GLS-beta mean.
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun)
+  python bench.py --impl reference --gpus N --steps K --warmup W
+
+A step = one pass of the hot path over one batch of B seeded candidates per GPU
+(X = maximin 100 pts, y = simulator 4, sigma2 = 1, candidates
+(psi1, psi2, phi, zeta) from default_rng(20131 + rank)).  `value` is timed with CUDA
+events on the launching stream, inputs resident in HBM, max over ranks; `e2e` is the
+same metric through the host-pointer C-ABI call (H2D of the candidates + D2H of
+nll/beta/status inside the timed region).  One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_PTS, DIM = 100, 2
+# F_nll(n,d) = P*c_pair + (n^3/3 + n^2/2 + n/6) + 2n^2 + 6n, c_pair = 4d+3 (aniso), + 2P exp
+P_PAIRS = N_PTS * (N_PTS - 1) // 2
+FLOP_PER_EVAL = P_PAIRS * (4 * DIM + 3) + (N_PTS ** 3 / 3 + N_PTS ** 2 / 2 + N_PTS / 6) + 2 * N_PTS ** 2 + 6 * N_PTS
+EXP_PER_EVAL = 2 * P_PAIRS
+BYTES_PER_EVAL = 52  # 32 B candidate row in, nll + beta + status out
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=1 << 20, help="candidates per GPU per step")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="candidates in the CPU-baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-me", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------ CPU arm (oracle = the reference's algorithm)
+def _cpu_worker(args):
+    os.environ["OPENBLAS_NUM_THREADS"] = "1"
+    from oracle import ccgp_oracle as orc
+    X, y, s2, th = args
+    out = np.empty(len(th))
+    for i, t in enumerate(th):
+        nat = orc.transform_theta(orc.FAMILY_ANISO_LAMBDA, t, 2)
+        out[i] = orc.loglik_reference(X, y, s2, orc.FAMILY_ANISO_LAMBDA, nat)["loglik"]
+    return out
+
+
+class CpuArm:
+    """The reference's per-candidate algorithm (LU inverse + beta.MLE + dmnorm: chol, chol2inv) via the
+    oracle port on every host core, one single-threaded-BLAS worker process per core."""
+
+    def __init__(self):
+        import multiprocessing as mp
+        from ccgp_b200 import workloads
+        self.cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
+        self.X, self.y, self.s2 = workloads.m1_design()
+        os.environ["OPENBLAS_NUM_THREADS"] = "1"
+        self.pool = mp.get_context("fork").Pool(self.cores)
+        self.workloads = workloads
+
+    def run(self, th):
+        chunks = np.array_split(th, self.cores * 4)
+        t0 = time.perf_counter()
+        res = self.pool.map(_cpu_worker, [(self.X, self.y, self.s2, c) for c in chunks if len(c)])
+        dt = time.perf_counter() - t0
+        return dt, np.concatenate(res)
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def blas_name():
+    try:
+        import scipy
+        cfg = scipy.show_config(mode="dicts")
+        b = cfg["Build Dependencies"]["blas"]
+        return "%s %s" % (b.get("name"), b.get("version"))
+    except Exception:
+        return "scipy-bundled BLAS/LAPACK"
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    arm = CpuArm()
+    per_step = max(256, 256 * arm.cores)
+    th_all = arm.workloads.m1_candidates(per_step * (args.steps + args.warmup))
+    k = 0
+    for _ in range(args.warmup):
+        arm.run(th_all[k:k + per_step]); k += per_step
+    total = 0.0
+    for _ in range(args.steps):
+        dt, _ = arm.run(th_all[k:k + per_step]); k += per_step
+        total += dt
+    arm.close()
+    val = per_step * args.steps / total
+    line = {
+        "impl": "reference", "metric": "combined-GP NLL evals/sec (batched, n=100)", "value": val, "unit": "evals/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "M1: n=100 d=2 anisotropic GLS-beta NLL (maximin 100 pts, simulator 4, sigma2=1)",
+                   "candidates_per_step": per_step},
+        "cpu_baseline": {"value": val, "unit": "evals/s", "cores": arm.cores, "kind": "port",
+                         "sample": "%d candidates/step of the M1 stream, reference-faithful path (dgesv+dgecon inverse, "
+                                   "dpotrf+dpotri dmnorm), 1 process/core, %s" % (per_step, blas_name())},
+        "e2e": {"value": val, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, row in self.rows:
+            if ts < t0 or ts > t1 + 0.2:
+                continue
+            f = [x.strip() for x in row.split(",")]
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except Exception:
+                continue
+            for nm, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------ GPU arm
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    import ccgp_b200
+    from ccgp_b200 import workloads, sharding, GAUSS_ANISO_LAMBDA, LOGSCALE
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    eng = ccgp_b200.Engine(local_rank)
+    stream = torch.cuda.current_stream(dev)
+    eng.set_stream(stream.cuda_stream)
+    X, y, s2 = workloads.m1_design()
+    eng.set_design(X, y)
+    B = args.batch
+    th_host = workloads.m1_candidates(B, seed=20131 + rank)          # B x 4, real-line scale
+    cand_pinned = torch.from_numpy(np.asfortranarray(th_host).T.copy()).pin_memory()   # 4 x B row-major == B x 4 col-major
+    cand_dev = cand_pinned.to(dev)
+    nll = torch.empty(B, dtype=torch.float64, device=dev)
+    beta = torch.empty(B, dtype=torch.float64, device=dev)
+    status = torch.empty(B, dtype=torch.int32, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def step():
+        eng.nll_batch_dev(cand_dev, GAUSS_ANISO_LAMBDA, s2, scale=LOGSCALE, out_nll=nll, out_beta=beta, out_status=status)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    peak = eng.measure_fp64_peak()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = eng.launch_count
+    barrier()
+    t_wall0 = time.perf_counter()
+    evs = []
+    for _ in range(args.steps):
+        flush.zero_()                                # L2 flush between timed iterations (outside the event pair)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        step()
+        e1.record(stream)
+        evs.append((e0, e1))
+    barrier()
+    t_wall1 = time.perf_counter()
+    launches = eng.launch_count - launches0
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    total_ms = float(sum(step_ms))
+    # the path's only collective: which.min of the likelihood over all ranks (value, global index)
+    bv, bi = eng.argmin_dev(nll)
+    gmin = sharding.allreduce_argmin(bv, bi + rank * B if bi >= 0 else -1, device=dev)
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    n_bad = int((status != 0).sum().item())
+
+    # ---- e2e: host buffers through the C-ABI host entry point, copies inside the timed region
+    th_f = np.asfortranarray(th_host)
+    eng.set_stream(None)
+    eng.nll_batch(th_f, GAUSS_ANISO_LAMBDA, s2, scale=LOGSCALE)
+    barrier()
+    t0 = time.perf_counter()
+    ksteps = max(3, min(args.steps, 10))
+    for _ in range(ksteps):
+        h_nll, h_beta, h_st = eng.nll_batch(th_f, GAUSS_ANISO_LAMBDA, s2, scale=LOGSCALE)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    assert np.array_equal(h_nll, nll.cpu().numpy()), "host-pointer path and device path disagree"
+    cfg = eng.last_nll_config()
+
+    # ---- M2: ME subset (Schur) determinants/sec, pool(1000) x params(1000) per step, resident inputs
+    me = None
+    if not args.no_me:
+        eng.set_stream(stream.cuda_stream)
+        D_old, pool = workloads.me_pool()
+        P = 1000
+        params = workloads.me_params(P, seed=7 + rank)
+        d_old = torch.from_numpy(np.asfortranarray(D_old).T.copy()).to(dev)
+        d_new = torch.from_numpy(np.ascontiguousarray(pool.transpose(0, 2, 1))).to(dev)
+        d_par = torch.from_numpy(np.asfortranarray(params).T.copy()).to(dev)
+        negdet = torch.empty(1000 * P, dtype=torch.float64, device=dev)
+        for _ in range(3):
+            eng.me_schur_batch_dev(d_old, 14, 2, d_new, 7, 1000, d_par, P, negdet)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        me_steps = 5
+        for _ in range(me_steps):
+            eng.me_schur_batch_dev(d_old, 14, 2, d_new, 7, 1000, d_par, P, negdet)
+        e1.record(stream)
+        barrier()
+        me_ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([me_ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            me_ms = float(t.item())
+        me = {"metric": "ME subset (Schur) log-dets/sec", "value": world * 1000 * P * me_steps / (me_ms * 1e-3),
+              "unit": "dets/s", "workload": "ME-A: Initial ME Design (14x2) + 1000 All_Subdesigns blocks x 1000 parameter rows per GPU per step",
+              "ms_per_step": me_ms / me_steps}
+        eng.set_stream(None)
+
+    # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        arm = CpuArm()
+        ns = args.cpu_sample or max(2048, 2048 * arm.cores // 8 * 1)
+        ns = min(ns, B)
+        arm.run(th_host[:min(ns, 256)])
+        dt, ll = arm.run(th_host[:ns])
+        arm.close()
+        got = -nll[:ns].cpu().numpy()
+        relerr = float(np.max(np.abs(got - ll) / np.maximum(np.abs(ll), 1.0)))
+        cpu = {"value": ns / dt, "unit": "evals/s", "cores": arm.cores, "kind": "port",
+               "sample": "first %d candidates of the step's batch, reference-faithful oracle path (dgesv+dgecon inverse, "
+                         "dpotrf+dpotri dmnorm), 1 process/core, %s" % (ns, blas_name()),
+               "max_rel_err_gpu_vs_cpu": relerr}
+
+    if rank == 0:
+        secs = total_ms * 1e-3
+        evals = world * B * args.steps
+        value = evals / secs
+        kern_s = (total_ms / args.steps) * 1e-3                     # one kernel launch per step per GPU
+        achieved_tf = FLOP_PER_EVAL * B / kern_s / 1e12
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get("nll_kernel_dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {
+            "metric": "combined-GP NLL evals/sec (batched, n=100)", "value": value, "unit": "evals/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "M1: n=100 d=2 anisotropic GLS-beta NLL (maximin 100 pts, simulator 4, sigma2=1)",
+                       "candidates_per_gpu_per_step": B, "parallelism": "candidates sharded, dp%d" % world,
+                       "l2": "flushed between timed steps (256 MiB memset outside the event pairs); working set/step = %d MiB"
+                             % ((B * BYTES_PER_EVAL) >> 20),
+                       "kernel": cfg, "not_pd_candidates": n_bad,
+                       "argmin": {"nll": gmin[0], "index": gmin[1]}},
+            "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak / 1e12, "unit": "TFLOP/s",
+                         "frac": achieved_tf / (peak / 1e12),
+                         "peak_source": "measured live: dependent-free DFMA loop on all SMs (MEASURED_PEAKS.json has no FP64 entry)",
+                         "flop_per_eval": FLOP_PER_EVAL, "exp_per_eval": EXP_PER_EVAL,
+                         "exp_per_s": EXP_PER_EVAL * B / kern_s,
+                         "hbm": {"achieved_gbs": BYTES_PER_EVAL * B / kern_s / 1e9, "peak_gbs": hbm_peak,
+                                 "frac": BYTES_PER_EVAL * B / kern_s / 1e9 / hbm_peak},
+                         "traffic": traffic},
+            "cpu_baseline": cpu,
+            "e2e": {"value": world * B * ksteps / e2e_s, "unit": "evals/s", "h2d_bytes_per_step": int(B * 32),
+                    "d2h_bytes_per_step": int(B * 20), "timed": "wall clock around %d synchronous ccgp_nll_batch host calls" % ksteps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "me": me,
+        }
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        # plain `python bench.py --gpus N`: re-launch under torchrun, one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", str(29400 + os.getpid() % 500)] + sys.argv
+        sys.exit(subprocess.call(cmd))
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

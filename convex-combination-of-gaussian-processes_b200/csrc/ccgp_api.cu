@@ -1,0 +1,819 @@
+// ccgp_api.cu -- the C ABI of libccgp.so (include/ccgp.h) over the sm_100a kernels.
+// Host side only does bookkeeping: argument checks, the shared design and
+// decode tables in HBM, kernel-variant choice, H2D/D2H for the host-pointer
+// entry points.  There is no CPU compute path.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <map>
+#include <vector>
+#include <algorithm>
+#include "../../include/ccgp.h"
+#include "factor_engine.cuh"
+#include "predict_kernel.cuh"
+#include "me_kernel.cuh"
+#include "bigchol.cuh"
+
+using namespace ccgp;
+
+struct ccgp_ctx {
+    int device = 0;
+    int num_sm = 0;
+    int max_smem_optin = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;
+    int n = 0, d = 0;
+    double* d_X = nullptr;
+    double* d_y = nullptr;
+    std::map<std::pair<int, int>, uint32_t*> ijtabs;  // (n, naug) -> decode table
+    void* ws = nullptr;       // device workspace for the host-pointer entry points
+    size_t ws_bytes = 0;
+    void* ws2 = nullptr;      // small device workspace (params, reductions)
+    size_t ws2_bytes = 0;
+    char err[512] = {0};
+    int64_t launches = 0;
+    int last_team = 0, last_smem = 0, last_ctas = 0, last_variant = -1;
+    BigCholWorkspace big;
+};
+
+static char g_create_err[512] = "";
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            snprintf(ctx->err, sizeof(ctx->err), "%s:%d %s: %s", __FILE__, __LINE__, #call,        \
+                     cudaGetErrorString(e_));                                                      \
+            return CCGP_ERR_CUDA;                                                                  \
+        }                                                                                          \
+    } while (0)
+
+#define RC(call)                                                                                   \
+    do {                                                                                           \
+        int rc_ = (call);                                                                          \
+        if (rc_) return rc_;                                                                       \
+    } while (0)
+
+#define ARG(cond)                                                                                  \
+    do {                                                                                           \
+        if (!(cond)) {                                                                             \
+            snprintf(ctx->err, sizeof(ctx->err), "bad argument: %s", #cond);                       \
+            return CCGP_ERR_ARG;                                                                   \
+        }                                                                                          \
+    } while (0)
+
+static int env_int(const char* name, int dflt) {
+    const char* s = getenv(name);
+    return (s && *s) ? atoi(s) : dflt;
+}
+
+// ------------------------------------------------------------------ variants
+typedef void (*factor_fn)(const FactorArgs);
+struct Variant { int team, tr, ks, minb; factor_fn fn_d0, fn_d2; };
+
+#define CCGP_VARIANTS(X)                                                                           \
+    X(32, 2, 1, 16) X(32, 4, 1, 16) X(64, 4, 1, 8) X(64, 4, 2, 8) X(128, 4, 2, 4) X(128, 4, 4, 4)     \
+    X(128, 8, 4, 4) X(256, 4, 4, 2) X(256, 8, 4, 2) X(64, 2, 2, 8) X(128, 2, 4, 4) X(256, 4, 8, 2)    \
+    X(128, 4, 1, 4) X(128, 4, 4, 5) X(64, 2, 1, 8) X(256, 2, 8, 2)
+
+#define X(T, R, K, M) {T, R, K, M, factor_kernel<T, R, K, 0, M>, factor_kernel<T, R, K, 2, M>},
+static const Variant g_variants[] = {CCGP_VARIANTS(X)};
+#undef X
+static const int g_num_variants = sizeof(g_variants) / sizeof(g_variants[0]);
+
+static int default_variant(const Layout& l) {
+    if (l.npad <= 24) return 0;    // 32 x TR2
+    if (l.npad <= 40) return 1;    // 32 x TR4
+    if (l.npad <= 72) return 9;    // 64 x TR2 x KS2
+    if (l.npad <= 136) return 5;   // 128 x TR4 x KS4
+    return 7;                      // 256 x TR4 x KS4
+}
+
+static int get_ijtab(ccgp_ctx* ctx, const Layout& l, const uint32_t** out) {
+    auto key = std::make_pair(l.n, l.naug);
+    auto it = ctx->ijtabs.find(key);
+    if (it != ctx->ijtabs.end()) { *out = it->second; return 0; }
+    std::vector<uint32_t> h((size_t)l.total);
+    size_t e = 0;
+    for (int J = 0; J < l.NJ; ++J)
+        for (int c = 0; c < 8; ++c)
+            for (int i = 8 * J; i < l.npad; ++i) h[e++] = (uint32_t)i | ((uint32_t)(8 * J + c) << 16);
+    uint32_t* dptr = nullptr;
+    CK(cudaMalloc(&dptr, h.size() * 4));
+    CK(cudaMemcpyAsync(dptr, h.data(), h.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->ijtabs[key] = dptr;
+    *out = dptr;
+    return 0;
+}
+
+static int ensure_ws(ccgp_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->ws_bytes) return 0;
+    if (ctx->ws) CK(cudaFree(ctx->ws));
+    ctx->ws = nullptr; ctx->ws_bytes = 0;
+    size_t want = std::max(bytes, (size_t)1 << 20);
+    CK(cudaMalloc(&ctx->ws, want));
+    ctx->ws_bytes = want;
+    return 0;
+}
+static int ensure_ws2(ccgp_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->ws2_bytes) return 0;
+    if (ctx->ws2) CK(cudaFree(ctx->ws2));
+    ctx->ws2 = nullptr; ctx->ws2_bytes = 0;
+    size_t want = std::max(bytes, (size_t)1 << 16);
+    CK(cudaMalloc(&ctx->ws2, want));
+    ctx->ws2_bytes = want;
+    return 0;
+}
+
+// choose variant + grid and launch the factor kernel
+static int launch_factor(ccgp_ctx* ctx, FactorArgs& A) {
+    const Layout& l = A.lay;
+    int v = env_int("CCGP_VARIANT", -1);
+    if (v < 0 || v >= g_num_variants) v = default_variant(l);
+    size_t smem = smem_bytes(l, A.d);
+    if (smem > (size_t)ctx->max_smem_optin) {
+        snprintf(ctx->err, sizeof(ctx->err), "n=%d needs %zu B shared memory (> %d)", l.n, smem, ctx->max_smem_optin);
+        return CCGP_ERR_UNSUPPORTED;
+    }
+    const Variant& var = g_variants[v];
+    // the row-slot passes need H/TR <= 32*G per pass only for efficiency; any size is correct
+    factor_fn fn = (A.d == 2) ? var.fn_d2 : var.fn_d0;
+    if (env_int("CCGP_NO_DT", 0)) fn = var.fn_d0;
+    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int nb = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, var.team, smem));
+    if (nb < 1) { snprintf(ctx->err, sizeof(ctx->err), "kernel variant %d does not fit", v); return CCGP_ERR_UNSUPPORTED; }
+    int64_t grid = (int64_t)nb * ctx->num_sm;
+    if (grid > A.W) grid = A.W;
+    if (grid < 1) return 0;
+    RC(get_ijtab(ctx, l, &A.ijtab));
+    fn<<<(unsigned)grid, var.team, smem, ctx->stream>>>(A);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    ctx->last_team = var.team; ctx->last_smem = (int)smem; ctx->last_ctas = nb; ctx->last_variant = v;
+    return 0;
+}
+
+// ------------------------------------------------------------------ context
+extern "C" int ccgp_num_params(int family, int d) {
+    if (family == CCGP_GAUSS_ISO || family == CCGP_GAUSS_ISO_RAW2) return 3;
+    if (family == CCGP_GAUSS_ANISO_LAMBDA) return d + 2;
+    return -1;
+}
+
+extern "C" int ccgp_create(ccgp_ctx** out, int device) {
+    if (!out) return CCGP_ERR_ARG;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count < 1) {
+        snprintf(g_create_err, sizeof(g_create_err), "no usable CUDA device (%s); libccgp has no CPU fallback",
+                 e != cudaSuccess ? cudaGetErrorString(e) : "count=0");
+        return CCGP_ERR_CUDA;
+    }
+    if (device < 0 || device >= count) {
+        snprintf(g_create_err, sizeof(g_create_err), "device %d out of range (0..%d)", device, count - 1);
+        return CCGP_ERR_ARG;
+    }
+    ccgp_ctx* ctx = new ccgp_ctx();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        snprintf(g_create_err, sizeof(g_create_err), "device init: %s", cudaGetErrorString(e));
+        delete ctx;
+        return CCGP_ERR_CUDA;
+    }
+    if (prop.major != 10) {
+        snprintf(g_create_err, sizeof(g_create_err), "libccgp is built for sm_100a only; device %d is sm_%d%d",
+                 device, prop.major, prop.minor);
+        cudaStreamDestroy(ctx->stream);
+        delete ctx;
+        return CCGP_ERR_UNSUPPORTED;
+    }
+    ctx->own_stream = ctx->stream;
+    ctx->num_sm = prop.multiProcessorCount;
+    ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    *out = ctx;
+    return CCGP_OK;
+}
+
+extern "C" int ccgp_destroy(ccgp_ctx* ctx) {
+    if (!ctx) return CCGP_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& kv : ctx->ijtabs) cudaFree(kv.second);
+    if (ctx->d_X) cudaFree(ctx->d_X);
+    if (ctx->d_y) cudaFree(ctx->d_y);
+    if (ctx->ws) cudaFree(ctx->ws);
+    if (ctx->ws2) cudaFree(ctx->ws2);
+    ctx->big.release();
+    cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return CCGP_OK;
+}
+
+extern "C" const char* ccgp_last_error(const ccgp_ctx* ctx) { return ctx ? ctx->err : g_create_err; }
+extern "C" int ccgp_device(const ccgp_ctx* ctx) { return ctx ? ctx->device : -1; }
+extern "C" int64_t ccgp_launch_count(const ccgp_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int ccgp_set_stream(ccgp_ctx* ctx, void* stream) {
+    if (!ctx) return CCGP_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->stream = stream ? (cudaStream_t)stream : ctx->own_stream;
+    return CCGP_OK;
+}
+
+extern "C" int ccgp_sync(ccgp_ctx* ctx) {
+    if (!ctx) return CCGP_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return CCGP_OK;
+}
+
+extern "C" int ccgp_last_nll_config(const ccgp_ctx* ctx, int* team, int* smem, int* ctas, int* variant) {
+    if (!ctx) return CCGP_ERR_ARG;
+    if (team) *team = ctx->last_team;
+    if (smem) *smem = ctx->last_smem;
+    if (ctas) *ctas = ctx->last_ctas;
+    if (variant) *variant = ctx->last_variant;
+    return CCGP_OK;
+}
+
+// ---- FP64 FMA peak: 8 independent chains per thread, all SMs ------------------
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, double seed) {
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 0.999999, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (s == 123.456) out[0] = s;
+}
+
+extern "C" int ccgp_measure_fp64_peak(ccgp_ctx* ctx, double* flops) {
+    if (!ctx || !flops) return CCGP_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    RC(ensure_ws2(ctx, 64));
+    const int iters = 1 << 15, blocks = ctx->num_sm * 8, threads = 256;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    double best = 0;
+    for (int rep = 0; rep < 4; ++rep) {
+        CK(cudaEventRecord(e0, ctx->stream));
+        dfma_peak_kernel<<<blocks, threads, 0, ctx->stream>>>((double*)ctx->ws2, iters, 1.0);
+        CK(cudaEventRecord(e1, ctx->stream));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        double f = 2.0 * 8.0 * iters * (double)blocks * threads / (ms * 1e-3);
+        if (rep > 0 && f > best) best = f;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *flops = best;
+    return CCGP_OK;
+}
+
+// ------------------------------------------------------------------ design
+extern "C" int ccgp_set_design(ccgp_ctx* ctx, const double* X, int n, int d, const double* y) {
+    if (!ctx) return CCGP_ERR_ARG;
+    ARG(X != nullptr && y != nullptr);
+    ARG(n >= 1 && n <= 32768);
+    ARG(d >= 1 && d <= MAXD);
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->d_X) { CK(cudaFree(ctx->d_X)); ctx->d_X = nullptr; }
+    if (ctx->d_y) { CK(cudaFree(ctx->d_y)); ctx->d_y = nullptr; }
+    CK(cudaMalloc(&ctx->d_X, (size_t)n * d * 8));
+    CK(cudaMalloc(&ctx->d_y, (size_t)n * 8));
+    CK(cudaMemcpyAsync(ctx->d_X, X, (size_t)n * d * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_y, y, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->n = n;
+    ctx->d = d;
+    return CCGP_OK;
+}
+
+// ------------------------------------------------------------------ NLL
+static int check_nll_args(ccgp_ctx* ctx, int family, int scale, const void* cand, int64_t B, int64_t ldc,
+                          double sigma2, int mean_mode) {
+    ARG(ctx->n > 0);
+    ARG(family >= 0 && family <= 2);
+    ARG(scale == 0 || scale == 1);
+    ARG(mean_mode == 0 || mean_mode == 1);
+    ARG(B >= 0 && ldc >= B);
+    ARG(B == 0 || cand != nullptr);
+    ARG(sigma2 > 0);
+    return 0;
+}
+
+extern "C" int ccgp_nll_batch_dev(ccgp_ctx* ctx, int family, int scale, const double* d_cand, int64_t B, int64_t ldc,
+                                  double sigma2, int mean_mode, double tau, double* d_nll, double* d_beta,
+                                  int32_t* d_status) {
+    if (!ctx) return CCGP_ERR_ARG;
+    int rc = check_nll_args(ctx, family, scale, d_cand, B, ldc, sigma2, mean_mode);
+    if (rc) return rc;
+    ARG(B == 0 || d_nll != nullptr);
+    if (B == 0) return CCGP_OK;
+    CK(cudaSetDevice(ctx->device));
+    Layout l = make_layout(ctx->n, 2);
+    if (smem_bytes(l, ctx->d) > (size_t)ctx->max_smem_optin || env_int("CCGP_FORCE_BIG", 0)) {
+        return bigchol_nll_batch(ctx->big, ctx->stream, ctx->num_sm, ctx->d_X, ctx->d_y, ctx->n, ctx->d, family, scale,
+                                 d_cand, B, ldc, sigma2, mean_mode, tau, d_nll, d_beta, d_status, &ctx->launches,
+                                 ctx->err, sizeof(ctx->err));
+    }
+    FactorArgs A;
+    memset(&A, 0, sizeof(A));
+    A.lay = l;
+    A.d = ctx->d;
+    A.design_mode = DESIGN_SHARED;
+    A.X = ctx->d_X;
+    A.y = ctx->d_y;
+    A.n_designs = 1;
+    A.tail0 = 0;
+    A.cand = d_cand;
+    A.ldc = ldc;
+    A.n_params = B;
+    A.family = family;
+    A.logscale = scale;
+    A.sigma2 = sigma2;
+    A.mean_mode = mean_mode;
+    A.tau = tau;
+    A.W = B;
+    A.out0 = d_nll;
+    A.out1 = d_beta;
+    A.status = d_status;
+    A.out_mode = OUT_NLL;
+    return launch_factor(ctx, A);
+}
+
+extern "C" int ccgp_nll_batch(ccgp_ctx* ctx, int family, int scale, const double* cand, int64_t B, int64_t ldc,
+                              double sigma2, int mean_mode, double tau, double* out_nll, double* out_beta,
+                              int32_t* out_status) {
+    if (!ctx) return CCGP_ERR_ARG;
+    int rc = check_nll_args(ctx, family, scale, cand, B, ldc, sigma2, mean_mode);
+    if (rc) return rc;
+    ARG(B == 0 || out_nll != nullptr);
+    if (B == 0) return CCGP_OK;
+    CK(cudaSetDevice(ctx->device));
+    const int k = ccgp_num_params(family, ctx->d);
+    // workspace: cand (B*k) | nll (B) | beta (B) | status (B int32)
+    size_t need = (size_t)B * (k + 2) * 8 + (size_t)B * 4;
+    if ((rc = ensure_ws(ctx, need))) return rc;
+    double* d_cand = (double*)ctx->ws;
+    double* d_nll = d_cand + (size_t)B * k;
+    double* d_beta = d_nll + B;
+    int32_t* d_status = (int32_t*)(d_beta + B);
+    if (ldc == B) {
+        CK(cudaMemcpyAsync(d_cand, cand, (size_t)B * k * 8, cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        CK(cudaMemcpy2DAsync(d_cand, (size_t)B * 8, cand, (size_t)ldc * 8, (size_t)B * 8, k, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    rc = ccgp_nll_batch_dev(ctx, family, scale, d_cand, B, B, sigma2, mean_mode, tau, d_nll, d_beta, d_status);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out_nll, d_nll, (size_t)B * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_beta) CK(cudaMemcpyAsync(out_beta, d_beta, (size_t)B * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_status) CK(cudaMemcpyAsync(out_status, d_status, (size_t)B * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return CCGP_OK;
+}
+
+// ---- argmin (which.min: first index of the minimum, NaN skipped) --------------
+struct MinIdx { double v; long long i; };
+__device__ __forceinline__ MinIdx better(MinIdx a, MinIdx b) {
+    // a NaN value never wins; ties go to the lower index
+    bool bw = (b.i >= 0) && (a.i < 0 || b.v < a.v || (b.v == a.v && b.i < a.i));
+    return bw ? b : a;
+}
+__device__ __forceinline__ MinIdx block_min(MinIdx m, MinIdx* sh) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        MinIdx t;
+        t.v = __shfl_xor_sync(0xffffffffu, m.v, o);
+        t.i = __shfl_xor_sync(0xffffffffu, m.i, o);
+        m = better(m, t);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) sh[warp] = m;
+    __syncthreads();
+    if (warp == 0) {
+        m = (lane < (int)(blockDim.x >> 5)) ? sh[lane] : MinIdx{0.0, -1};
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            MinIdx t;
+            t.v = __shfl_xor_sync(0xffffffffu, m.v, o);
+            t.i = __shfl_xor_sync(0xffffffffu, m.i, o);
+            m = better(m, t);
+        }
+    }
+    return m;
+}
+// column q of a C x P column-major matrix -> partial (val, idx) per block
+__global__ void __launch_bounds__(256) argmin_partial_kernel(const double* v, int64_t C, MinIdx* part) {
+    __shared__ MinIdx sh[8];
+    const int64_t q = blockIdx.y;
+    const double* col = v + q * C;
+    MinIdx m{0.0, -1};
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < C; i += (int64_t)gridDim.x * blockDim.x) {
+        double x = col[i];
+        if (x == x) m = better(m, MinIdx{x, (long long)i});
+    }
+    m = block_min(m, sh);
+    if (threadIdx.x == 0) part[q * gridDim.x + blockIdx.x] = m;
+}
+__global__ void __launch_bounds__(256) argmin_final_kernel(const MinIdx* part, int nparts, double* best_val, long long* best_idx) {
+    __shared__ MinIdx sh[8];
+    const int64_t q = blockIdx.x;
+    MinIdx m{0.0, -1};
+    for (int i = threadIdx.x; i < nparts; i += blockDim.x) m = better(m, part[q * nparts + i]);
+    m = block_min(m, sh);
+    if (threadIdx.x == 0) {
+        best_val[q] = (m.i >= 0) ? m.v : __longlong_as_double(0x7ff8000000000000LL);
+        best_idx[q] = m.i;
+    }
+}
+
+// argmin of each of P columns (length C) of a device matrix; results to host
+static int argmin_columns(ccgp_ctx* ctx, const double* d_vals, int64_t C, int64_t P, double* best_val, int64_t* best_idx) {
+    int nparts = (int)std::min<int64_t>((C + 255) / 256, 256);
+    if (nparts < 1) nparts = 1;
+    size_t need = (size_t)P * nparts * sizeof(MinIdx) + (size_t)P * 16;
+    int rc = ensure_ws2(ctx, need);
+    if (rc) return rc;
+    MinIdx* part = (MinIdx*)ctx->ws2;
+    double* d_bv = (double*)(part + (size_t)P * nparts);
+    long long* d_bi = (long long*)(d_bv + P);
+    for (int64_t q0 = 0; q0 < P; q0 += 65535) {
+        int64_t pq = std::min<int64_t>(65535, P - q0);
+        argmin_partial_kernel<<<dim3(nparts, (unsigned)pq), 256, 0, ctx->stream>>>(d_vals + q0 * C, C, part + q0 * nparts);
+        CK(cudaGetLastError());
+        ctx->launches++;
+    }
+    argmin_final_kernel<<<(unsigned)P, 256, 0, ctx->stream>>>(part, nparts, d_bv, d_bi);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    std::vector<long long> hi((size_t)P);
+    CK(cudaMemcpyAsync(best_val, d_bv, (size_t)P * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(hi.data(), d_bi, (size_t)P * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int64_t q = 0; q < P; ++q) best_idx[q] = (int64_t)hi[q];
+    return 0;
+}
+
+extern "C" int ccgp_argmin_dev(ccgp_ctx* ctx, const double* d_vals, int64_t B, double* best_val, int64_t* best_idx) {
+    if (!ctx) return CCGP_ERR_ARG;
+    ARG(d_vals != nullptr && B >= 1 && best_val != nullptr && best_idx != nullptr);
+    CK(cudaSetDevice(ctx->device));
+    return argmin_columns(ctx, d_vals, B, 1, best_val, best_idx);
+}
+
+extern "C" int ccgp_nll_argmin(ccgp_ctx* ctx, int family, int scale, const double* cand, int64_t B, int64_t ldc,
+                               double sigma2, int mean_mode, double tau, double* best_nll, int64_t* best_idx) {
+    if (!ctx) return CCGP_ERR_ARG;
+    int rc = check_nll_args(ctx, family, scale, cand, B, ldc, sigma2, mean_mode);
+    if (rc) return rc;
+    ARG(B >= 1 && best_nll != nullptr && best_idx != nullptr);
+    CK(cudaSetDevice(ctx->device));
+    const int k = ccgp_num_params(family, ctx->d);
+    size_t need = (size_t)B * (k + 1) * 8;
+    if ((rc = ensure_ws(ctx, need))) return rc;
+    double* d_cand = (double*)ctx->ws;
+    double* d_nll = d_cand + (size_t)B * k;
+    CK(cudaMemcpy2DAsync(d_cand, (size_t)B * 8, cand, (size_t)ldc * 8, (size_t)B * 8, k, cudaMemcpyHostToDevice, ctx->stream));
+    rc = ccgp_nll_batch_dev(ctx, family, scale, d_cand, B, B, sigma2, mean_mode, tau, d_nll, nullptr, nullptr);
+    if (rc) return rc;
+    return argmin_columns(ctx, d_nll, B, 1, best_nll, best_idx);
+}
+
+// ------------------------------------------------------------------ R.Inv
+extern "C" int ccgp_rinv_batch(ccgp_ctx* ctx, int family, int scale, const double* cand, int64_t B, int64_t ldc,
+                               double* out_Rinv, double* out_beta, int32_t* out_status) {
+    if (!ctx) return CCGP_ERR_ARG;
+    int rc = check_nll_args(ctx, family, scale, cand, B, ldc, 1.0, 0);
+    if (rc) return rc;
+    ARG(B == 0 || out_Rinv != nullptr);
+    if (B == 0) return CCGP_OK;
+    CK(cudaSetDevice(ctx->device));
+    const int n = ctx->n, k = ccgp_num_params(family, ctx->d);
+    Layout l = make_layout(n, 2);
+    constexpr int TEAM = 128;
+    size_t smem = rinv_smem_bytes<TEAM>(l, ctx->d);
+    if (smem > (size_t)ctx->max_smem_optin) {
+        snprintf(ctx->err, sizeof(ctx->err), "ccgp_rinv_batch: n=%d exceeds the shared-memory path", n);
+        return CCGP_ERR_UNSUPPORTED;
+    }
+    size_t need = (size_t)B * k * 8 + (size_t)B * n * n * 8 + (size_t)B * 8 + (size_t)B * 4;
+    if ((rc = ensure_ws(ctx, need))) return rc;
+    double* d_cand = (double*)ctx->ws;
+    double* d_rinv = d_cand + (size_t)B * k;
+    double* d_beta = d_rinv + (size_t)B * n * n;
+    int32_t* d_status = (int32_t*)(d_beta + B);
+    CK(cudaMemcpy2DAsync(d_cand, (size_t)B * 8, cand, (size_t)ldc * 8, (size_t)B * 8, k, cudaMemcpyHostToDevice, ctx->stream));
+    RinvArgs P;
+    memset(&P, 0, sizeof(P));
+    FactorArgs& A = P.F;
+    A.lay = l; A.d = ctx->d; A.design_mode = DESIGN_SHARED; A.X = ctx->d_X; A.y = ctx->d_y; A.n_designs = 1;
+    A.cand = d_cand; A.ldc = B; A.n_params = B; A.family = family; A.logscale = scale; A.sigma2 = 1.0; A.W = B;
+    A.out_mode = OUT_NLL;
+    RC(get_ijtab(ctx, l, &A.ijtab));
+    P.out_rinv = d_rinv; P.out_beta = d_beta; P.status = d_status;
+    auto fn = rinv_kernel<TEAM, 4, 4, 2>;
+    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t grid = std::min<int64_t>(B, (int64_t)ctx->num_sm * 2);
+    fn<<<(unsigned)grid, TEAM, smem, ctx->stream>>>(P);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    CK(cudaMemcpyAsync(out_Rinv, d_rinv, (size_t)B * n * n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_beta) CK(cudaMemcpyAsync(out_beta, d_beta, (size_t)B * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_status) CK(cudaMemcpyAsync(out_status, d_status, (size_t)B * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return CCGP_OK;
+}
+
+// ------------------------------------------------------------------ predict
+template <int TEAM, int TR, int KS, int MR, int MINB>
+static int launch_predict(ccgp_ctx* ctx, PredictArgs& P) {
+    constexpr int TP = 4;
+    const Layout& l = P.F.lay;
+    size_t smem = predict_smem_bytes<TEAM, TP>(l, P.F.d);
+    if (smem > (size_t)ctx->max_smem_optin) {
+        snprintf(ctx->err, sizeof(ctx->err), "ccgp_predict: n=%d exceeds the shared-memory path", l.n);
+        return CCGP_ERR_UNSUPPORTED;
+    }
+    auto fn = predict_kernel<TEAM, TR, KS, 0, MR, TP, MINB>;
+    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int nb = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, TEAM, smem));
+    if (nb < 1) nb = 1;
+    int64_t grid = std::min<int64_t>(P.F.W, (int64_t)nb * ctx->num_sm);
+    fn<<<(unsigned)grid, TEAM, smem, ctx->stream>>>(P);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    return 0;
+}
+
+extern "C" int ccgp_predict_dev(ccgp_ctx* ctx, int family, const double* d_pars, int64_t S, int64_t ldp,
+                                int vec_family, const double* d_pars_vec, int64_t ldpv, const double* d_Xnew,
+                                int64_t T, double sigma2, double* d_mean, double* d_var, int32_t* d_status) {
+    if (!ctx) return CCGP_ERR_ARG;
+    ARG(ctx->n > 0);
+    ARG(family >= 0 && family <= 2);
+    ARG(S >= 0 && T >= 0 && ldp >= S);
+    ARG(sigma2 > 0);
+    if (S == 0 || T == 0) return CCGP_OK;
+    ARG(d_pars && d_Xnew && d_mean && d_var);
+    ARG(d_pars_vec == nullptr || (vec_family >= 0 && vec_family <= 2 && ldpv >= S));
+    CK(cudaSetDevice(ctx->device));
+    PredictArgs P;
+    memset(&P, 0, sizeof(P));
+    FactorArgs& A = P.F;
+    A.lay = make_layout(ctx->n, 2);
+    A.d = ctx->d; A.design_mode = DESIGN_SHARED; A.X = ctx->d_X; A.y = ctx->d_y; A.n_designs = 1;
+    A.cand = d_pars; A.ldc = ldp; A.n_params = S; A.family = family; A.logscale = 0; A.sigma2 = sigma2; A.W = S;
+    A.out_mode = OUT_NLL;
+    int rc = get_ijtab(ctx, A.lay, &A.ijtab);
+    if (rc) return rc;
+    P.Xnew = d_Xnew; P.T = T; P.candv = d_pars_vec; P.ldcv = ldpv; P.vec_family = vec_family;
+    P.out_mean = d_mean; P.out_var = d_var; P.status = d_status;
+    const int n = ctx->n;
+    if (n <= 32) return launch_predict<64, 2, 1, 1, 8>(ctx, P);
+    if (n <= 64) return launch_predict<128, 2, 4, 2, 4>(ctx, P);
+    if (n <= 128) return launch_predict<128, 4, 4, 4, 4>(ctx, P);
+    if (n <= 256) return launch_predict<256, 4, 4, 8, 2>(ctx, P);
+    snprintf(ctx->err, sizeof(ctx->err), "ccgp_predict: n=%d > 256 not supported yet", n);
+    return CCGP_ERR_UNSUPPORTED;
+}
+
+extern "C" int ccgp_predict(ccgp_ctx* ctx, int family, const double* pars, int64_t S, int64_t ldp, int vec_family,
+                            const double* pars_vec, int64_t ldpv, const double* Xnew, int64_t T, double sigma2,
+                            double* out_mean, double* out_var, int32_t* out_status) {
+    if (!ctx) return CCGP_ERR_ARG;
+    ARG(ctx->n > 0);
+    ARG(S >= 0 && T >= 0 && ldp >= S);
+    if (S == 0 || T == 0) return CCGP_OK;
+    ARG(pars && Xnew && out_mean && out_var);
+    ARG(family >= 0 && family <= 2);
+    CK(cudaSetDevice(ctx->device));
+    const int d = ctx->d, k = ccgp_num_params(family, d);
+    const int kv = pars_vec ? ccgp_num_params(vec_family, d) : 0;
+    ARG(kv >= 0);
+    size_t need = ((size_t)S * (k + kv) + (size_t)T * d + 2 * (size_t)T * S) * 8 + (size_t)S * 4;
+    int rc = ensure_ws(ctx, need);
+    if (rc) return rc;
+    double* d_pars = (double*)ctx->ws;
+    double* d_pv = d_pars + (size_t)S * k;
+    double* d_xn = d_pv + (size_t)S * kv;
+    double* d_mean = d_xn + (size_t)T * d;
+    double* d_var = d_mean + (size_t)T * S;
+    int32_t* d_status = (int32_t*)(d_var + (size_t)T * S);
+    CK(cudaMemcpy2DAsync(d_pars, (size_t)S * 8, pars, (size_t)ldp * 8, (size_t)S * 8, k, cudaMemcpyHostToDevice, ctx->stream));
+    if (pars_vec) CK(cudaMemcpy2DAsync(d_pv, (size_t)S * 8, pars_vec, (size_t)ldpv * 8, (size_t)S * 8, kv, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_xn, Xnew, (size_t)T * d * 8, cudaMemcpyHostToDevice, ctx->stream));
+    rc = ccgp_predict_dev(ctx, family, d_pars, S, S, vec_family, pars_vec ? d_pv : nullptr, S, d_xn, T, sigma2, d_mean, d_var, d_status);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out_mean, d_mean, (size_t)T * S * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(out_var, d_var, (size_t)T * S * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_status) CK(cudaMemcpyAsync(out_status, d_status, (size_t)S * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return CCGP_OK;
+}
+
+// ------------------------------------------------------------------ ME criteria
+extern "C" int ccgp_me_schur_batch_dev(ccgp_ctx* ctx, const double* d_D_old, int n_old, int d, const double* d_D_new,
+                                       int n_new, int64_t C, const double* d_params, int64_t P, int64_t ldq,
+                                       double* d_negdet, double* d_logdet, int32_t* d_status) {
+    if (!ctx) return CCGP_ERR_ARG;
+    ARG(n_old >= 0 && n_new >= 1 && d >= 1 && d <= MAXD);
+    ARG(n_old == 0 || d_D_old != nullptr);
+    ARG(C >= 0 && P >= 0 && ldq >= P);
+    if (C == 0 || P == 0) return CCGP_OK;
+    ARG(d_D_new && d_params && (d_negdet || d_logdet));
+    CK(cudaSetDevice(ctx->device));
+    if (me_fast_supported(n_old, n_new, d) && !env_int("CCGP_ME_GENERIC", 0)) {
+        int rc = me_fast_launch(ctx->stream, ctx->num_sm, d_D_old, n_old, d, d_D_new, n_new, C, d_params, P, ldq,
+                                d_negdet, d_logdet, d_status, ctx->err, sizeof(ctx->err));
+        if (rc == 0) ctx->launches++;
+        return rc;
+    }
+    FactorArgs A;
+    memset(&A, 0, sizeof(A));
+    A.lay = make_layout(n_old + n_new, 0);
+    A.d = d;
+    A.design_mode = DESIGN_OLD_PLUS_NEW;
+    A.X = d_D_old; A.Dnew = d_D_new; A.n_old = n_old; A.tail0 = n_old;
+    A.n_designs = C;
+    A.cand = d_params; A.ldc = ldq; A.n_params = P; A.family = FAM_ISO; A.logscale = 0; A.sigma2 = 1.0;
+    A.W = C * P;
+    A.out0 = nullptr; A.out1 = d_logdet; A.out2 = d_negdet; A.status = d_status;
+    A.out_mode = OUT_DET;
+    // n_params == 1 means "shared row"; with P == 1 that is what we want too
+    return launch_factor(ctx, A);
+}
+
+extern "C" int ccgp_me_schur_batch(ccgp_ctx* ctx, const double* D_old, int n_old, int d, const double* D_new, int n_new,
+                                   int64_t C, const double* params, int64_t P, int64_t ldq, double* out_negdet,
+                                   double* out_logdet, int32_t* out_status) {
+    if (!ctx) return CCGP_ERR_ARG;
+    ARG(n_old >= 0 && n_new >= 1 && d >= 1 && d <= MAXD && C >= 0 && P >= 0 && ldq >= P);
+    if (C == 0 || P == 0) return CCGP_OK;
+    ARG(D_new && params && (out_negdet || out_logdet));
+    ARG(n_old == 0 || D_old != nullptr);
+    CK(cudaSetDevice(ctx->device));
+    size_t nold_d = (size_t)n_old * d, nnew = (size_t)C * n_new * d, npar = (size_t)P * 3, nout = (size_t)C * P;
+    size_t need = (nold_d + nnew + npar + 2 * nout) * 8 + nout * 4;
+    int rc = ensure_ws(ctx, need);
+    if (rc) return rc;
+    double* d_old = (double*)ctx->ws;
+    double* d_new = d_old + nold_d;
+    double* d_par = d_new + nnew;
+    double* d_neg = d_par + npar;
+    double* d_log = d_neg + nout;
+    int32_t* d_st = (int32_t*)(d_log + nout);
+    if (n_old) CK(cudaMemcpyAsync(d_old, D_old, nold_d * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_new, D_new, nnew * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpy2DAsync(d_par, (size_t)P * 8, params, (size_t)ldq * 8, (size_t)P * 8, 3, cudaMemcpyHostToDevice, ctx->stream));
+    rc = ccgp_me_schur_batch_dev(ctx, d_old, n_old, d, d_new, n_new, C, d_par, P, P, d_neg, d_log, d_st);
+    if (rc) return rc;
+    if (out_negdet) CK(cudaMemcpyAsync(out_negdet, d_neg, nout * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_logdet) CK(cudaMemcpyAsync(out_logdet, d_log, nout * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_status) CK(cudaMemcpyAsync(out_status, d_st, nout * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return CCGP_OK;
+}
+
+extern "C" int ccgp_me_argmin(ccgp_ctx* ctx, const double* D_old, int n_old, int d, const double* D_new, int n_new,
+                              int64_t C, const double* params, int64_t P, int64_t ldq, double* best_val,
+                              int64_t* best_idx) {
+    if (!ctx) return CCGP_ERR_ARG;
+    ARG(n_old >= 0 && n_new >= 1 && d >= 1 && d <= MAXD && C >= 1 && P >= 1 && ldq >= P);
+    ARG(D_new && params && best_val && best_idx);
+    ARG(n_old == 0 || D_old != nullptr);
+    CK(cudaSetDevice(ctx->device));
+    size_t nold_d = (size_t)n_old * d, nnew = (size_t)C * n_new * d, npar = (size_t)P * 3, nout = (size_t)C * P;
+    size_t need = (nold_d + nnew + npar + nout) * 8;
+    int rc = ensure_ws(ctx, need);
+    if (rc) return rc;
+    double* d_old = (double*)ctx->ws;
+    double* d_new = d_old + nold_d;
+    double* d_par = d_new + nnew;
+    double* d_neg = d_par + npar;
+    if (n_old) CK(cudaMemcpyAsync(d_old, D_old, nold_d * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_new, D_new, nnew * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpy2DAsync(d_par, (size_t)P * 8, params, (size_t)ldq * 8, (size_t)P * 8, 3, cudaMemcpyHostToDevice, ctx->stream));
+    rc = ccgp_me_schur_batch_dev(ctx, d_old, n_old, d, d_new, n_new, C, d_par, P, P, d_neg, nullptr, nullptr);
+    if (rc) return rc;
+    return argmin_columns(ctx, d_neg, C, P, best_val, best_idx);
+}
+
+// ------------------------------------------------------------------ subset log-dets
+extern "C" int ccgp_subset_logdet_batch_dev(ccgp_ctx* ctx, const double* d_pool, int64_t N, int d, const int32_t* d_idx,
+                                            int m, int64_t C, int64_t ldi, int family, const double* params_host,
+                                            double* d_logdet, int32_t* d_status) {
+    if (!ctx) return CCGP_ERR_ARG;
+    ARG(N >= 1 && d >= 1 && d <= MAXD && m >= 1 && m <= N && C >= 0 && ldi >= C);
+    ARG(family >= 0 && family <= 2);
+    if (C == 0) return CCGP_OK;
+    ARG(d_pool && d_idx && params_host && d_logdet);
+    CK(cudaSetDevice(ctx->device));
+    const int k = ccgp_num_params(family, d);
+    int rc = ensure_ws2(ctx, 64 * 8);
+    if (rc) return rc;
+    // params live at the END of ws2's first 64 doubles so argmin scratch (front) never collides mid-stream
+    double* d_par = (double*)ctx->ws2;
+    CK(cudaMemcpyAsync(d_par, params_host, (size_t)k * 8, cudaMemcpyHostToDevice, ctx->stream));
+    FactorArgs A;
+    memset(&A, 0, sizeof(A));
+    A.lay = make_layout(m, 0);
+    A.d = d;
+    A.design_mode = DESIGN_GATHER;
+    A.X = d_pool; A.ldpool = N; A.idx = d_idx; A.ldi = ldi; A.tail0 = 0;
+    A.n_designs = C;
+    A.cand = d_par; A.ldc = 1; A.n_params = 1; A.family = family; A.logscale = 0; A.sigma2 = 1.0;
+    A.W = C;
+    A.out0 = d_logdet; A.status = d_status;
+    A.out_mode = OUT_DET;
+    return launch_factor(ctx, A);
+}
+
+extern "C" int ccgp_subset_logdet_batch(ccgp_ctx* ctx, const double* pool, int64_t N, int d, const int32_t* idx, int m,
+                                        int64_t C, int64_t ldi, int family, const double* params, double* out_logdet,
+                                        int32_t* out_status) {
+    if (!ctx) return CCGP_ERR_ARG;
+    ARG(N >= 1 && d >= 1 && d <= MAXD && m >= 1 && m <= N && C >= 0 && ldi >= C);
+    if (C == 0) return CCGP_OK;
+    ARG(pool && idx && params && out_logdet);
+    CK(cudaSetDevice(ctx->device));
+    size_t need = (size_t)N * d * 8 + (size_t)C * m * 4 + 8 + (size_t)C * 8 + (size_t)C * 4;
+    int rc = ensure_ws(ctx, need);
+    if (rc) return rc;
+    double* d_pool = (double*)ctx->ws;
+    double* d_out = d_pool + (size_t)N * d;
+    int32_t* d_idx = (int32_t*)(d_out + C);
+    int32_t* d_st = d_idx + (size_t)C * m;
+    CK(cudaMemcpyAsync(d_pool, pool, (size_t)N * d * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpy2DAsync(d_idx, (size_t)C * 4, idx, (size_t)ldi * 4, (size_t)C * 4, m, cudaMemcpyHostToDevice, ctx->stream));
+    rc = ccgp_subset_logdet_batch_dev(ctx, d_pool, N, d, d_idx, m, C, C, family, params, d_out, d_st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out_logdet, d_out, (size_t)C * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_status) CK(cudaMemcpyAsync(out_status, d_st, (size_t)C * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return CCGP_OK;
+}
+
+// ------------------------------------------------------------------ plain correlation blocks
+// out[i + na*j] = mixed correlation of A_i and B_j: Mixed.corr.matrix (A=B=D.train, [A]:399-406),
+// Mixed.corr.vec (A = x.new, [A]:416-422) and cross.corr.matrix ([M]:835-848, p=1).
+__global__ void __launch_bounds__(256) mixed_corr_kernel(FactorArgs F, const double* Am, int na, const double* Bm, int nb, double* out, int same) {
+    __shared__ Prm prm;
+    if (threadIdx.x == 0) load_params(F, 0, &prm);
+    __syncthreads();
+    const int d = F.d;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < (int64_t)na * nb; e += (int64_t)gridDim.x * blockDim.x) {
+        int i = (int)(e % na), j = (int)(e / na);
+        double s1 = 0.0;
+        for (int k = 0; k < d; ++k) {
+            double df = Am[i + (int64_t)na * k] - Bm[j + (int64_t)nb * k];
+            s1 = fma(prm.wts[k] * df, df, s1);
+        }
+        double v = fma(prm.b, dexp_neg(prm.rho * s1), prm.a * dexp_neg(s1));
+        if (same && i == j) v = 1.0;
+        out[e] = v;
+    }
+}
+
+extern "C" int ccgp_mixed_corr(ccgp_ctx* ctx, int family, const double* params, const double* A, int na,
+                               const double* B, int nb, int d, double* out) {
+    if (!ctx) return CCGP_ERR_ARG;
+    ARG(family >= 0 && family <= 2 && params && A && out && na >= 1 && d >= 1 && d <= MAXD);
+    ARG(B == nullptr || nb >= 1);
+    CK(cudaSetDevice(ctx->device));
+    const int same = (B == nullptr);
+    if (same) nb = na;
+    const int k = ccgp_num_params(family, d);
+    size_t need = ((size_t)k + (size_t)na * d + (same ? 0 : (size_t)nb * d) + (size_t)na * nb) * 8;
+    RC(ensure_ws(ctx, need));
+    double* d_par = (double*)ctx->ws;
+    double* d_A = d_par + k;
+    double* d_B = same ? d_A : d_A + (size_t)na * d;
+    double* d_out = d_B + (size_t)nb * d;
+    CK(cudaMemcpyAsync(d_par, params, (size_t)k * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_A, A, (size_t)na * d * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (!same) CK(cudaMemcpyAsync(d_B, B, (size_t)nb * d * 8, cudaMemcpyHostToDevice, ctx->stream));
+    FactorArgs F;
+    memset(&F, 0, sizeof(F));
+    F.d = d; F.cand = d_par; F.ldc = 1; F.n_params = 1; F.family = family; F.logscale = 0; F.sigma2 = 1.0;
+    int64_t tot = (int64_t)na * nb;
+    int grid = (int)std::min<int64_t>((tot + 255) / 256, (int64_t)ctx->num_sm * 8);
+    mixed_corr_kernel<<<grid, 256, 0, ctx->stream>>>(F, d_A, na, d_B, nb, d_out, same);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    CK(cudaMemcpyAsync(out, d_out, (size_t)na * nb * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return CCGP_OK;
+}

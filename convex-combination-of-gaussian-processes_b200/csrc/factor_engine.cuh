@@ -1,0 +1,470 @@
+// factor_engine.cuh -- fused covariance-build + Cholesky + forward solves, one
+// CTA ("team") per candidate, the whole FP64 factor resident in shared memory.
+//
+// Replaces, per candidate, the body of the reference's `logpost` up to
+// `log.like` ([A]:444-455: Mixed.corr.matrix -> solve(R) -> beta.MLE -> dmnorm)
+// and of `cond.like` ([V]:564-575), and -- in determinant mode -- `Entropy`
+// ([M]:856-861) / `Augmented.Mixed.Entropy` ([M]:869-877) / subset log-dets.
+//
+// Algorithm (SURVEY Appendix B "minimal NLL"):
+//   A = [ R ; y' ; 1' ]  (n+2 rows, n columns; R by direct differences, unit diag)
+//   left-looking blocked Cholesky, panel width 8: the two extra rows come out as
+//   z_y = L^-1 y and z_1 = L^-1 1, so the triangular solves are free.
+//   beta = z_1.z_y / z_1.z_1,  Q_R = |z_y - beta z_1|^2,  log det R = sum log piv.
+//
+// Shared-memory layout of L ("block-column trapezoid"): block column J (8 wide)
+// stores rows 8J..npad-1 column-major with height H_J = npad-8J, block columns
+// back to back.  Every column start is 16-byte aligned so rows are read as
+// double2; a column of L is contiguous in its row index, so the K-loop row
+// loads of consecutive lanes are consecutive 16-byte words (conflict-free) and
+// the 8 panel-row values are warp-wide broadcasts.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "ccgp_math.h"
+
+namespace ccgp {
+
+constexpr int MAXD = 16;
+// a Cholesky pivot of the unit-diagonal R at or below 2 eps means kappa(R) > 1/(2 eps): the
+// analogue of base R's `solve` refusing rcond < .Machine$double.eps ([A]:448-449 -> NA)
+constexpr double PIVOT_MIN = 4.440892098500626e-16;
+constexpr double LOG2PI = 1.8378770664093454835606594728112;
+constexpr double LN2 = 0.69314718055994530941723212145818;
+
+enum { FAM_ISO = 0, FAM_ANISO = 1, FAM_ISO_RAW2 = 2 };
+enum { OUT_NLL = 0, OUT_DET = 1 };
+enum { DESIGN_SHARED = 0, DESIGN_OLD_PLUS_NEW = 1, DESIGN_GATHER = 2 };
+
+struct Prm {  // per-candidate parameters, one copy in shared memory
+    double wts[MAXD];  // component-1 per-dimension scales theta_k
+    double rho;        // component-2 exponent = rho * component-1 exponent
+    double a, b;       // p^2/w, (1-p)^2/w
+    double c;          // w * sigma2
+    double p;
+};
+
+struct Layout {
+    int n;      // design points
+    int naug;   // 0 (determinant mode) or 2 (rows y and 1)
+    int npad;   // n + naug rounded up to 8
+    int NJ;     // block columns = ceil(n / 8)
+    int total;  // doubles of L storage
+    int npx;    // leading dimension of the staged design (n rounded up to 2)
+};
+
+__host__ __device__ __forceinline__ int blk_base(int J, int npad) { return 8 * (J * npad - 4 * J * (J - 1)); }
+
+inline Layout make_layout(int n, int naug) {
+    Layout l;
+    l.n = n;
+    l.naug = naug;
+    l.npad = (n + naug + 7) / 8 * 8;
+    l.NJ = (n + 7) / 8;
+    l.total = blk_base(l.NJ, l.npad);
+    l.npx = (n + 1) / 2 * 2;
+    return l;
+}
+
+// shared bytes: L | Xs[d*npx] | ys[npx] | rinv[8] | red[64] | Prm | ints[4]
+inline size_t smem_bytes(const Layout& l, int d) {
+    size_t dbl = (size_t)l.total + (size_t)d * l.npx + l.npx + 8 + 64;
+    return dbl * 8 + sizeof(Prm) + 16;
+}
+
+struct FactorArgs {
+    Layout lay;
+    int d;
+    int design_mode;
+    const double* X;      // SHARED: n x d (ld n); OLD_PLUS_NEW: D_old n_old x d (ld n_old); GATHER: pool (ld ldpool)
+    const double* y;      // SHARED + naug
+    const double* Dnew;   // OLD_PLUS_NEW: design c at Dnew + c*n_new*d, n_new x d column-major
+    const int32_t* idx;   // GATHER: idx[c + ldi*r]
+    int64_t ldi;
+    int64_t ldpool;
+    int n_old;            // OLD_PLUS_NEW: rows of D_old
+    int tail0;            // pivots j >= tail0 form the "tail" determinant
+    int64_t n_designs;
+    const double* cand;   // n_params x k column-major, ld ldc
+    int64_t ldc;
+    int64_t n_params;
+    int family;
+    int logscale;
+    double sigma2;
+    int mean_mode;
+    double tau;
+    int64_t W;            // work items: w -> design w % n_designs, parameter row w / n_designs
+    const uint32_t* ijtab;
+    double* out0;         // NLL: nll          DET: log det (all pivots)
+    double* out1;         // NLL: beta         DET: log det (tail pivots)
+    double* out2;         // DET: -det(tail) (negated determinant, the ME criterion value)
+    int32_t* status;
+    int out_mode;
+};
+
+template <int TEAM>
+__device__ __forceinline__ void team_sync() {
+    if (TEAM == 32) __syncwarp(); else __syncthreads();
+}
+
+__device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
+
+// running product of pivots kept as mantissa in [1,2) and an integer exponent
+__device__ __forceinline__ void prod_accum(double& mant, int& es, double piv) {
+    mant *= piv;
+    int hi = __double2hiint(mant);
+    int e = ((hi >> 20) & 0x7ff) - 1023;
+    es += e;
+    mant = __hiloint2double(hi - (e << 20), __double2loint(mant));
+}
+
+__device__ inline void load_params(const FactorArgs& A, int64_t pi, Prm* prm) {
+    const double* c = A.cand + pi;
+    const int64_t ld = A.ldc;
+    const int d = A.d;
+    double p, rho;
+    if (A.family == FAM_ANISO) {
+        double lam;
+        if (A.logscale) {
+            for (int k = 0; k < d; ++k) prm->wts[k] = exp(c[k * ld]);
+            p = 1.0 / (1.0 + exp(-c[d * ld]));
+            lam = exp(c[(d + 1) * ld]);
+        } else {
+            p = c[0];
+            for (int k = 0; k < d; ++k) prm->wts[k] = c[(k + 1) * ld];
+            lam = c[(d + 1) * ld];
+        }
+        rho = 1.0 + lam;
+    } else {
+        double t1, t2;
+        if (A.logscale) {
+            t1 = exp(c[0]);
+            t2 = exp(c[ld]);
+            p = 1.0 / (1.0 + exp(-c[2 * ld]));
+        } else {
+            p = c[0];
+            t1 = c[ld];
+            t2 = c[2 * ld];
+        }
+        for (int k = 0; k < d; ++k) prm->wts[k] = t1;
+        rho = t2 / t1;
+    }
+    double w = p * p + (1.0 - p) * (1.0 - p);
+    prm->rho = rho;
+    prm->a = p * p / w;
+    prm->b = (1.0 - p) * (1.0 - p) / w;
+    prm->c = w * A.sigma2;
+    prm->p = p;
+}
+
+// mixed correlation of points i and j of the staged design
+template <int DT>
+__device__ __forceinline__ double mixed_corr(const double* Xs, int npx, int d, int i, int j,
+                                             const double* wts, double rho, double a, double b) {
+    double s1 = 0.0;
+    if (DT > 0) {
+#pragma unroll
+        for (int k = 0; k < DT; ++k) {
+            double df = Xs[k * npx + i] - Xs[k * npx + j];
+            s1 = fma(wts[k] * df, df, s1);
+        }
+    } else {
+        for (int k = 0; k < d; ++k) {
+            double df = Xs[k * npx + i] - Xs[k * npx + j];
+            s1 = fma(wts[k] * df, df, s1);
+        }
+    }
+    double e1 = dexp_neg(s1);
+    double e2 = dexp_neg(rho * s1);
+    return fma(b, e2, a * e1);
+}
+
+struct FactorResult {  // valid in thread 0 of the team after factor_candidate()
+    double mant_all, mant_tail;
+    int es_all, es_tail;
+    int bad;
+};
+
+// Build A into Ls and factor it in place.  All threads of the team call this.
+template <int TEAM, int TR, int KS, int DT>
+__device__ __forceinline__ FactorResult factor_candidate(const FactorArgs& A, double* Ls, const double* Xs,
+                                                         const double* ys, double* rinv_s, const Prm* prm) {
+    static_assert(TR == 2 || TR == 4 || TR == 8, "TR");
+    static_assert((TEAM / 32) % KS == 0, "KS must divide the warp count");
+    constexpr int G = (TEAM / 32) / KS;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int ks = warp % KS;
+    const int g = warp / KS;
+    const int n = A.lay.n, npad = A.lay.npad, NJ = A.lay.NJ, naug = A.lay.naug, npx = A.lay.npx, d = A.d;
+
+    // ---- build: every stored slot (i,j) of the trapezoid ---------------------
+    {
+        double wts[DT > 0 ? DT : 1];
+        if (DT > 0) {
+#pragma unroll
+            for (int k = 0; k < DT; ++k) wts[k] = prm->wts[k];
+        }
+        const double rho = prm->rho, a = prm->a, b = prm->b;
+        for (int e = tid; e < A.lay.total; e += TEAM) {
+            uint32_t ij = __ldg(A.ijtab + e);
+            int i = ij & 0xffff, j = ij >> 16;
+            double v;
+            if (j >= n || i < j) v = 0.0;
+            else if (i == j) v = 1.0;
+            else if (i < n) v = mixed_corr<DT>(Xs, npx, d, i, j, DT > 0 ? wts : prm->wts, rho, a, b);
+            else if (naug && i == n) v = ys[j];
+            else if (naug && i == n + 1) v = 1.0;
+            else v = 0.0;
+            Ls[e] = v;
+        }
+    }
+    team_sync<TEAM>();
+
+    FactorResult res;
+    res.mant_all = 1.0; res.mant_tail = 1.0; res.es_all = 0; res.es_tail = 0; res.bad = 0;
+
+    for (int J = 0; J < NJ; ++J) {
+        const int H = npad - 8 * J;
+        const int pbase = blk_base(J, npad);
+        // ---- left-looking update of panel J with block columns < J -------------
+        if (J > 0) {
+            const int Q = H / TR;
+            for (int q0 = 0; q0 < Q; q0 += G * 32) {
+                const int q = q0 + g * 32 + lane;
+                const bool act = (q < Q) && (ks < J);
+                double acc[TR][8];
+#pragma unroll
+                for (int r = 0; r < TR; ++r)
+#pragma unroll
+                    for (int cc = 0; cc < 8; ++cc) acc[r][cc] = 0.0;
+                if (act) {
+                    for (int J2 = ks; J2 < J; J2 += KS) {
+                        const int H2 = npad - 8 * J2;
+                        const double* colp = Ls + blk_base(J2, npad) - 8 * J2 + 8 * J;
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            const double* cp = colp + c * H2;
+                            double2 l0 = ld2(cp), l1 = ld2(cp + 2), l2 = ld2(cp + 4), l3 = ld2(cp + 6);
+                            double lc[8] = {l0.x, l0.y, l1.x, l1.y, l2.x, l2.y, l3.x, l3.y};
+#pragma unroll
+                            for (int m = 0; m < TR / 2; ++m) {
+                                double2 lr = ld2(cp + 2 * (q + Q * m));
+#pragma unroll
+                                for (int cc = 0; cc < 8; ++cc) {
+                                    acc[2 * m][cc] = fma(-lr.x, lc[cc], acc[2 * m][cc]);
+                                    acc[2 * m + 1][cc] = fma(-lr.y, lc[cc], acc[2 * m + 1][cc]);
+                                }
+                            }
+                        }
+                    }
+                }
+                // deterministic reduction of the KS partial sums into the panel
+#pragma unroll
+                for (int r = 0; r < KS; ++r) {
+                    if (act && ks == r) {
+#pragma unroll
+                        for (int m = 0; m < TR / 2; ++m)
+#pragma unroll
+                            for (int cc = 0; cc < 8; ++cc) {
+                                double2* dst = reinterpret_cast<double2*>(Ls + pbase + cc * H + 2 * (q + Q * m));
+                                double2 v = *dst;
+                                v.x += acc[2 * m][cc];
+                                v.y += acc[2 * m + 1][cc];
+                                *dst = v;
+                            }
+                    }
+                    team_sync<TEAM>();
+                }
+            }
+        }
+        // ---- F1: factor the 8x8 diagonal block (warp 0; lane r <-> row 8J+r) ----
+        if (warp == 0) {
+            const int r = lane & 7;
+            double a8[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) a8[c] = Ls[pbase + c * H + r];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const double piv = __shfl_sync(0xffffffffu, a8[c], c);
+                const int j = 8 * J + c;
+                double ri = 0.0;
+                if (j < n) {
+                    ri = rsqrt(piv);
+                    if (!(piv > PIVOT_MIN)) res.bad = 1;
+                    prod_accum(res.mant_all, res.es_all, piv);
+                    if (j >= A.tail0) prod_accum(res.mant_tail, res.es_tail, piv);
+                }
+                const double l = (r == c) ? piv * ri : a8[c] * ri;
+                a8[c] = l;
+#pragma unroll
+                for (int c2 = c + 1; c2 < 8; ++c2) {
+                    const double lc2 = __shfl_sync(0xffffffffu, l, c2);
+                    a8[c2] = fma(-l, lc2, a8[c2]);
+                }
+                if (lane == 0) rinv_s[c] = ri;
+            }
+            if (lane < 8) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    if (c <= r) Ls[pbase + c * H + r] = a8[c];
+            }
+        }
+        team_sync<TEAM>();
+        // ---- F2: rows below the diagonal block, one thread per row -------------
+        if (H > 8) {
+            double ljj[28];
+            double ri[8];
+            {
+                int t = 0;
+#pragma unroll
+                for (int c = 1; c < 8; ++c)
+#pragma unroll
+                    for (int c1 = 0; c1 < c; ++c1) ljj[t++] = Ls[pbase + c1 * H + c];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) ri[c] = rinv_s[c];
+            }
+            for (int t = tid; t < H - 8; t += TEAM) {
+                double* p = Ls + pbase + 8 + t;
+                double x[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) x[c] = p[c * H];
+                int u = 0;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+#pragma unroll
+                    for (int c1 = 0; c1 < c; ++c1) x[c] = fma(-x[c1], ljj[u++], x[c]);
+                    x[c] *= ri[c];
+                }
+#pragma unroll
+                for (int c = 0; c < 8; ++c) p[c * H] = x[c];
+            }
+        }
+        team_sync<TEAM>();
+    }
+    return res;
+}
+
+__device__ __forceinline__ int elem_off(int i, int k, int npad) {
+    int J = k >> 3;
+    return blk_base(J, npad) + (k & 7) * (npad - 8 * J) + i - 8 * J;
+}
+
+// deterministic team-wide sum of two values; result returned to every thread
+template <int TEAM>
+__device__ __forceinline__ void team_sum2(double& u, double& v, double* red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        u += __shfl_xor_sync(0xffffffffu, u, o);
+        v += __shfl_xor_sync(0xffffffffu, v, o);
+    }
+    if (TEAM > 32) {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        __syncthreads();
+        if (lane == 0) { red[2 * warp] = u; red[2 * warp + 1] = v; }
+        __syncthreads();
+        u = 0.0; v = 0.0;
+#pragma unroll
+        for (int w = 0; w < TEAM / 32; ++w) { u += red[2 * w]; v += red[2 * w + 1]; }
+    }
+}
+
+template <int TEAM>
+__device__ __forceinline__ void stage_design(const FactorArgs& A, int64_t dsg, double* Xs) {
+    const int n = A.lay.n, npx = A.lay.npx, d = A.d;
+    if (A.design_mode == DESIGN_OLD_PLUS_NEW) {
+        const int n_old = A.n_old, n_new = n - n_old;
+        const double* Dn = A.Dnew + dsg * (int64_t)(n_new * d);
+        for (int e = threadIdx.x; e < n * d; e += TEAM) {
+            int k = e / n, i = e - k * n;
+            Xs[k * npx + i] = (i < n_old) ? A.X[k * n_old + i] : Dn[k * n_new + (i - n_old)];
+        }
+    } else if (A.design_mode == DESIGN_GATHER) {
+        for (int e = threadIdx.x; e < n * d; e += TEAM) {
+            int k = e / n, i = e - k * n;
+            int64_t src = A.idx[dsg + A.ldi * i];
+            Xs[k * npx + i] = A.X[k * A.ldpool + src];
+        }
+    }
+}
+
+template <int TEAM, int TR, int KS, int DT, int MINB>
+__global__ void __launch_bounds__(TEAM, MINB) factor_kernel(const FactorArgs A) {
+    extern __shared__ __align__(16) double smem[];
+    const Layout& lay = A.lay;
+    double* Ls = smem;
+    double* Xs = Ls + lay.total;
+    double* ys = Xs + A.d * lay.npx;
+    double* rinv_s = ys + lay.npx;
+    double* red = rinv_s + 8;
+    Prm* prm = reinterpret_cast<Prm*>(red + 64);
+    const int tid = threadIdx.x;
+    const int n = lay.n, npad = lay.npad;
+
+    if (A.design_mode == DESIGN_SHARED) {
+        for (int e = tid; e < n * A.d; e += TEAM) {
+            int k = e / n, i = e - k * n;
+            Xs[k * lay.npx + i] = A.X[e];
+        }
+        if (lay.naug) for (int i = tid; i < n; i += TEAM) ys[i] = A.y[i];
+    }
+
+    for (int64_t w = blockIdx.x; w < A.W; w += gridDim.x) {
+        team_sync<TEAM>();  // previous candidate fully consumed
+        const int64_t dsg = w % A.n_designs;
+        const int64_t pi = (A.n_params == 1) ? 0 : w / A.n_designs;
+        if (tid == 0) load_params(A, pi, prm);
+        if (A.design_mode != DESIGN_SHARED) stage_design<TEAM>(A, dsg, Xs);
+        team_sync<TEAM>();
+
+        FactorResult res = factor_candidate<TEAM, TR, KS, DT>(A, Ls, Xs, ys, rinv_s, prm);
+
+        if (A.out_mode == OUT_NLL) {
+            double s11 = 0.0, s1y = 0.0;
+            for (int k = tid; k < n; k += TEAM) {
+                int off = elem_off(n, k, npad);
+                double zy = Ls[off], z1 = Ls[off + 1];
+                s11 = fma(z1, z1, s11);
+                s1y = fma(z1, zy, s1y);
+            }
+            team_sum2<TEAM>(s11, s1y, red);
+            const double beta = s1y / s11;
+            double qr = 0.0, dummy = 0.0;
+            for (int k = tid; k < n; k += TEAM) {
+                int off = elem_off(n, k, npad);
+                double rz = fma(-beta, Ls[off + 1], Ls[off]);
+                qr = fma(rz, rz, qr);
+            }
+            team_sum2<TEAM>(qr, dummy, red);
+            if (tid == 0) {
+                const double c = prm->c;
+                const double logdet = log(res.mant_all) + res.es_all * LN2;
+                double nll;
+                if (A.mean_mode == 0) {
+                    nll = 0.5 * (qr / c + n * LOG2PI + n * log(c) + logdet);
+                } else {
+                    const double g = 1.0 + A.tau * A.tau * s11 / c;
+                    const double quad = qr / c + s1y * s1y / (c * s11 * g);
+                    nll = 0.5 * (quad + n * LOG2PI + n * log(c) + logdet + log(g));
+                }
+                const bool bad = res.bad || !(nll == nll);
+                const double nanv = __longlong_as_double(0x7ff8000000000000LL);
+                A.out0[w] = bad ? nanv : nll;
+                if (A.out1) A.out1[w] = bad ? nanv : beta;
+                if (A.status) A.status[w] = bad ? 1 : 0;
+            }
+        } else {
+            if (tid == 0) {
+                const double nanv = __longlong_as_double(0x7ff8000000000000LL);
+                const bool bad = res.bad != 0;
+                if (A.out0) A.out0[w] = bad ? nanv : log(res.mant_all) + res.es_all * LN2;
+                if (A.out1) A.out1[w] = bad ? nanv : log(res.mant_tail) + res.es_tail * LN2;
+                if (A.out2) A.out2[w] = bad ? nanv : -scalbn(res.mant_tail, res.es_tail);
+                if (A.status) A.status[w] = bad ? 1 : 0;
+            }
+        }
+    }
+}
+
+}  // namespace ccgp

@@ -1,0 +1,340 @@
+"""GPU (-m gpu): the CUDA path, called through the C ABI, against the oracle.
+
+Tolerances (BASELINE.json north_star): NLL, beta, predictive mean/var within
+1e-10 RELATIVE (|gpu-ref| <= 1e-10 * max(|ref|, 1)) of the reference-faithful
+oracle on candidates with kappa_1(R) <= 1e6; for the zero-mean + tau^2 variant the
+gate is the 50-digit truth (the reference's own direct factorisation is the less
+accurate path there) plus "no worse than the reference".
+ME selection: identical argmin index.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import ccgp_b200
+from ccgp_b200 import GAUSS_ISO, GAUSS_ANISO_LAMBDA, GAUSS_ISO_RAW2, LOGSCALE, MEAN_ZERO_PLUS_TAU2, workloads
+from ccgp_b200 import reference_api as api
+from oracle import ccgp_oracle as orc
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def test_native_library_is_loaded(engine):
+    maps = open("/proc/self/maps").read()
+    assert "libccgp.so" in maps
+    assert engine.measure_fp64_peak() > 1e12
+
+
+# ---------------------------------------------------------------- NLL vs golden
+def test_nll_c1_n100_aniso_golden(engine, golden, designs):
+    engine.set_design(designs["maximin100"], golden["c1n100_y"])
+    nll, beta, st = engine.nll_batch(golden["c1n100_nat"], GAUSS_ANISO_LAMBDA, 1.0)
+    assert np.all(st == 0)
+    assert rel_err(-nll, golden["c1n100_ref"]).max() < TOL
+    assert rel_err(beta, golden["c1n100_beta"]).max() < TOL
+    ok = ~np.isnan(golden["c1n100_truth"])
+    assert rel_err(-nll[ok], golden["c1n100_truth"][ok]).max() < TOL
+    # same candidates handed over on logpost's real-line scale: in-kernel transform
+    nll2, beta2, _ = engine.nll_batch(golden["c1n100_theta"], GAUSS_ANISO_LAMBDA, 1.0, scale=LOGSCALE)
+    assert rel_err(nll2, nll).max() < 1e-12
+
+
+def test_logpost_wrapper_matches_oracle(engine, golden, designs):
+    X = designs["maximin100"]
+    r = api.logpost_batch(X, golden["c1n100_theta"][:8], golden["c1n100_y"], 1.0, script="A", engine=engine)
+    assert rel_err(r["val"], golden["c1n100_logpost_val"]).max() < TOL
+    one = api.logpost(X, golden["c1n100_theta"][0], golden["c1n100_y"], 1.0, script="A", engine=engine)
+    assert rel_err(one["val"], golden["c1n100_logpost_val"][0]) < TOL
+    o = orc.logpost(X, golden["c1n100_theta"][0], golden["c1n100_y"], 1.0, orc.FAMILY_ANISO_LAMBDA, "A")
+    # R.Inv entries: relative to the largest entry, budget kappa * eps
+    assert np.abs(one["R_Inv"] - o["R_inv"]).max() / np.abs(o["R_inv"]).max() < 1e-10
+    assert rel_err(one["beta"], o["beta"]) < TOL
+
+
+@pytest.mark.parametrize("case,key,n_s2", [("c1n14gls", "maximin14", 0.7), ("c2gls", "he_train", 30.0),
+                                           ("gv50", "gv50_train1", 13.0), ("gv90", "gv90_train1", 13.0)])
+def test_nll_iso_gls_golden(engine, golden, designs, case, key, n_s2):
+    D = designs[key]
+    if key == "maximin14":
+        X, y, nat = D, golden["c1n14_y"], golden["c1n14_nat"]
+    elif key == "he_train":
+        X, y, nat = D[:, :4], D[:, 4], golden["c2_nat"]
+    else:
+        X, y, nat = D[:, :9], D[:, 9], golden[case + "_nat"]
+    engine.set_design(X, y)
+    nll, beta, st = engine.nll_batch(nat, GAUSS_ISO, n_s2)
+    ok = golden[case + "_kappa"] <= 1e6
+    assert np.all(st[ok] == 0)
+    assert rel_err(-nll[ok], golden[case + "_ref"][ok]).max() < TOL
+    assert rel_err(beta[ok], golden[case + "_beta"][ok]).max() < 1e-9   # beta carries kappa*eps directly
+    tr = golden[case + "_truth"]
+    okt = ~np.isnan(tr)
+    assert rel_err(-nll[okt], tr[okt]).max() < TOL
+
+
+@pytest.mark.parametrize("case,key,s2,tau", [("c1n14", "maximin14", 0.7, 100.0), ("c2tau", "he_train", 30.0, 50.0)])
+def test_nll_tau_variant_vs_truth(engine, golden, designs, case, key, s2, tau):
+    D = designs[key]
+    if key == "maximin14":
+        X, y, nat = D, golden["c1n14_y"], golden["c1n14_nat"]
+    else:
+        X, y, nat = D[:, :4], D[:, 4], golden["c2_nat"]
+    engine.set_design(X, y)
+    nll, _, st = engine.nll_batch(nat, GAUSS_ISO, s2, mean_mode=MEAN_ZERO_PLUS_TAU2, tau=tau)
+    assert np.all(st == 0)
+    tr = golden[case + "_truth"]
+    okt = ~np.isnan(tr)
+    e_gpu = rel_err(-nll[okt], tr[okt]).max()
+    e_ref = rel_err(golden[case + "_ref"][okt], tr[okt]).max()
+    assert e_gpu < TOL and e_gpu <= max(e_ref, 1e-13)
+    # and against the oracle's minimal (same algorithm) path on every row
+    assert rel_err(-nll, golden[case + "_minimal"]).max() < TOL
+
+
+def test_every_kernel_variant_agrees(engine, golden, designs):
+    """All tile/team variants of the factor kernel give the same numbers (the tuner may pick any)."""
+    engine.set_design(designs["maximin100"], golden["c1n100_y"])
+    base = None
+    try:
+        for v in range(16):
+            os.environ["CCGP_VARIANT"] = str(v)
+            nll, beta, st = engine.nll_batch(golden["c1n100_nat"], GAUSS_ANISO_LAMBDA, 1.0)
+            assert np.all(st == 0), v
+            assert rel_err(-nll, golden["c1n100_ref"]).max() < TOL, v
+            if base is None:
+                base = nll
+            assert rel_err(nll, base).max() < 1e-12, v
+        os.environ["CCGP_NO_DT"] = "1"
+        nll, _, _ = engine.nll_batch(golden["c1n100_nat"], GAUSS_ANISO_LAMBDA, 1.0)
+        assert rel_err(nll, base).max() < 1e-12
+    finally:
+        os.environ.pop("CCGP_VARIANT", None)
+        os.environ.pop("CCGP_NO_DT", None)
+
+
+# ---------------------------------------------------------------- fresh seeded inputs vs oracle
+@pytest.mark.parametrize("n,d,family", [(1, 1, GAUSS_ISO), (2, 2, GAUSS_ISO), (7, 3, GAUSS_ISO), (8, 2, GAUSS_ANISO_LAMBDA),
+                                        (9, 1, GAUSS_ISO), (16, 2, GAUSS_ANISO_LAMBDA), (23, 9, GAUSS_ISO),
+                                        (40, 4, GAUSS_ANISO_LAMBDA), (63, 2, GAUSS_ISO_RAW2), (64, 2, GAUSS_ISO),
+                                        (65, 5, GAUSS_ISO), (127, 2, GAUSS_ANISO_LAMBDA), (150, 3, GAUSS_ISO),
+                                        (200, 2, GAUSS_ANISO_LAMBDA)])
+def test_nll_random_designs_vs_oracle(engine, n, d, family):
+    rng = np.random.default_rng(1000 + n)
+    X = rng.uniform(-1, 1, (n, d))
+    y = np.sin(3 * X[:, 0]) + 0.3 * rng.normal(size=n)
+    B = 6
+    scale = 3.0 * n ** (1.0 / d)          # keeps R well conditioned as n grows
+    if family == GAUSS_ANISO_LAMBDA:
+        nat = np.column_stack([rng.uniform(0.1, 0.9, B)] + [scale * rng.uniform(1, 3, B) for _ in range(d)] + [rng.uniform(0.3, 2, B)])
+        of = orc.FAMILY_ANISO_LAMBDA
+    else:
+        nat = np.column_stack([rng.uniform(0.1, 0.9, B), scale * rng.uniform(1, 3, B), scale * rng.uniform(2, 6, B)])
+        of = orc.FAMILY_ISO if family == GAUSS_ISO else orc.FAMILY_ISO_RAW2
+    engine.set_design(X, y)
+    nll, beta, st = engine.nll_batch(nat, family, 1.7)
+    nll_t, _, _ = engine.nll_batch(nat, family, 1.7, mean_mode=MEAN_ZERO_PLUS_TAU2, tau=25.0)
+    for b in range(B):
+        o = orc.loglik_reference(X, y, 1.7, of, nat[b])
+        kappa = orc.cond1(orc.Mixed_corr_matrix_direct(X, of, nat[b]))
+        assert kappa < 1e6
+        assert st[b] == 0
+        assert rel_err(-nll[b], o["loglik"]) < TOL, (n, d, b)
+        assert rel_err(beta[b], o["beta"]) < 1e-9
+        m = orc.loglik_minimal(X, y, 1.7, of, nat[b], "tau", 25.0)
+        assert rel_err(-nll_t[b], m["loglik"]) < TOL
+
+
+def test_edge_cases(engine):
+    rng = np.random.default_rng(0)
+    X = rng.uniform(0, 1, (12, 2))
+    y = rng.normal(size=12)
+    engine.set_design(X, y)
+    # empty batch
+    nll, beta, st = engine.nll_batch(np.zeros((0, 3)), GAUSS_ISO, 1.0)
+    assert nll.shape == (0,)
+    # wrong column count is an argument error, not a crash
+    with pytest.raises(ValueError):
+        engine.nll_batch(np.ones((2, 5)), GAUSS_ISO, 1.0)
+    with pytest.raises(ccgp_b200.CcgpError):
+        engine.nll_batch(np.ones((2, 3)), GAUSS_ISO, -1.0)
+    # duplicated design point -> singular R -> NaN + status 1 (R: try(solve(R)) -> NA, [A]:448-449)
+    Xd = X.copy()
+    Xd[5] = Xd[2]
+    engine.set_design(Xd, y)
+    nll, beta, st = engine.nll_batch([[0.5, 2.0, 5.0], [0.3, 1.0, 9.0]], GAUSS_ISO, 1.0)
+    assert np.all(st == 1) and np.all(np.isnan(nll)) and np.all(np.isnan(beta))
+    assert orc.loglik_reference(Xd, y, 1.0, orc.FAMILY_ISO, [0.5, 2.0, 5.0])["status"] != 0
+    # p = 0 and p = 1 (a single component) are legal
+    engine.set_design(X, y)
+    nll, _, st = engine.nll_batch([[0.0, 2.0, 5.0], [1.0, 2.0, 5.0]], GAUSS_ISO, 1.0)
+    assert np.all(st == 0)
+    assert rel_err(-nll[0], orc.loglik_reference(X, y, 1.0, orc.FAMILY_ISO, [0.0, 2.0, 5.0])["loglik"]) < TOL
+    assert rel_err(-nll[1], orc.loglik_reference(X, y, 1.0, orc.FAMILY_ISO, [1.0, 2.0, 5.0])["loglik"]) < TOL
+
+
+# ---------------------------------------------------------------- full-size properties
+def test_full_size_properties_m1(engine):
+    """At the bench size: determinism, shard invariance, permutation invariance, argmin = which.min."""
+    X, y, s2 = workloads.m1_design()
+    B = 1 << 16
+    th = workloads.m1_candidates(B)
+    engine.set_design(X, y)
+    nll, beta, st = engine.nll_batch(th, GAUSS_ANISO_LAMBDA, s2, scale=LOGSCALE)
+    assert np.all(st == 0) and np.all(np.isfinite(nll))
+    nll2, _, _ = engine.nll_batch(th, GAUSS_ANISO_LAMBDA, s2, scale=LOGSCALE)
+    assert np.array_equal(nll, nll2)                                   # bit-reproducible
+    lo, hi = ccgp_b200.sharding.shard_range(B, 1, 4)
+    nll_s, _, _ = engine.nll_batch(th[lo:hi], GAUSS_ANISO_LAMBDA, s2, scale=LOGSCALE)
+    assert np.array_equal(nll_s, nll[lo:hi])                           # a shard computes the same bits
+    bv, bi = engine.nll_argmin(th, GAUSS_ANISO_LAMBDA, s2, scale=LOGSCALE)
+    assert bi == int(np.argmin(nll)) and bv == nll[bi]
+    # spot-check 12 rows against the oracle
+    rows = np.linspace(0, B - 1, 12).astype(int)
+    for b in rows:
+        o = orc.loglik_reference(X, y, s2, orc.FAMILY_ANISO_LAMBDA, orc.transform_theta(orc.FAMILY_ANISO_LAMBDA, th[b], 2))
+        assert rel_err(-nll[b], o["loglik"]) < TOL
+    # relabelling the design points leaves the likelihood unchanged (up to rounding)
+    perm = np.random.default_rng(5).permutation(100)
+    engine.set_design(X[perm], y[perm])
+    nll_p, _, _ = engine.nll_batch(th[:4096], GAUSS_ANISO_LAMBDA, s2, scale=LOGSCALE)
+    assert rel_err(nll_p, nll[:4096]).max() < 1e-11
+
+
+def test_choose_hyperpars_matches_oracle_rows(engine, golden, designs):
+    X = designs["maximin14"]
+    hp = designs["hyperpars_2d"]
+    N = int(golden["c1n14_likeli_N"])
+    rows = golden["c1n14_likeli_rows"].astype(int)
+    for i, want in zip(rows, golden["c1n14_likeli"]):
+        got = api.likeli_hyperpars(X, golden["c1n14_y"], hp[i, 0:2], hp[i, 2:4], 0.7, N=N, tau=100.0, engine=engine)
+        # the oracle's value carries the reference's own 1e-8 error in this variant; compare logs
+        assert abs(np.log(got) - np.log(want)) < 1e-6
+    res = api.choose_hyperpars(X, golden["c1n14_y"], hp, 0.7, N=1728, tau=100.0, engine=engine)
+    assert res["likelihoods"].shape == (60,) and np.all(res["likelihoods"] > 0)
+    assert np.array_equal(res["pars"], hp[int(np.argmax(res["likelihoods"]))])
+
+
+# ---------------------------------------------------------------- prediction
+def test_predict_golden_tables(engine, golden, designs):
+    engine.set_design(designs["maximin14"], golden["pred14_y"])
+    m, v, st = engine.predict(golden["pred14_pars"], GAUSS_ANISO_LAMBDA, golden["pred14_Xnew"], 0.9)
+    assert np.all(st == 0)
+    assert rel_err(m, golden["pred14_mean"]).max() < TOL
+    assert np.abs(v - golden["pred14_var"]).max() < 1e-9        # var ~ 1 - r'R^-1 r cancels: absolute, kappa*eps
+    # quirk Q2 ([V]:672)
+    m, v = api.predict_post_batch(golden["pred14_Xnew"], designs["maximin14"], golden["pred14_y"], golden["predV_pars"], 0.9,
+                                  script="V", engine=engine)
+    assert rel_err(m, golden["predV_mean"]).max() < TOL
+    assert np.abs(v - golden["predV_var"]).max() < 1e-9
+    he, het = designs["he_train"], designs["he_test"]
+    engine.set_design(he[:, :4], he[:, 4])
+    m, v, _ = engine.predict(golden["predHE_pars"], GAUSS_ISO, het[:, :4], 30.0)
+    assert rel_err(m, golden["predHE_mean"]).max() < 1e-9
+    assert np.abs(v - golden["predHE_var"]).max() / 30.0 < 1e-8
+    tr, te = designs["gv50_train1"], designs["gv50_test1"]
+    engine.set_design(tr[:, :9], tr[:, 9])
+    m, v, _ = engine.predict(golden["predGV_pars"], GAUSS_ISO, te[:20, :9], 13.0)
+    assert rel_err(m, golden["predGV_mean"]).max() < TOL
+    assert np.abs(v - golden["predGV_var"]).max() / 13.0 < 1e-9
+    one = api.predict_post(te[0, :9], tr[:, :9], tr[:, 9], golden["predGV_pars"][0], 13.0, script="G", engine=engine)
+    assert one.shape == (1, 2) and rel_err(one[0, 0], golden["predGV_mean"][0, 0]) < TOL
+
+
+def test_predict_interpolates_and_full_grid(engine):
+    """625-site grid x 64 posterior rows (the reference's T=25x25): at a training site the
+    mean is y_i and the variance ~0 (kriging interpolation) -- a size-independent property."""
+    X, y, _ = workloads.m1_design()
+    engine.set_design(X, y)
+    rng = np.random.default_rng(9)
+    S = 64
+    pars = np.column_stack([rng.uniform(0.2, 0.8, S), rng.uniform(15, 30, S), rng.uniform(15, 30, S), rng.uniform(0.5, 2, S)])
+    u = np.linspace(-1, 1, 25)
+    grid = np.array([[a, b] for b in u for a in u])
+    m, v, st = engine.predict(pars, GAUSS_ANISO_LAMBDA, np.vstack([grid, X[:10]]), 1.0)
+    assert np.all(st == 0) and m.shape == (635, S)
+    assert np.abs(m[625:] - y[:10, None]).max() < 1e-8
+    assert np.abs(v[625:]).max() < 1e-8
+    assert np.all(v[:625] > -1e-9)
+
+
+def test_mixed_corr_blocks(engine, designs):
+    X = designs["maximin14"]
+    R = api.Mixed_corr_matrix(X, 0.3, 2.0, 5.0, engine=engine)
+    assert np.abs(R - orc.Mixed_corr_matrix(X, orc.FAMILY_ISO, [0.3, 2.0, 5.0])).max() < 1e-13
+    Ra = api.Mixed_corr_matrix(X, 0.3, 2.0, 5.0, 1.5, engine=engine)
+    assert np.abs(Ra - orc.Mixed_corr_matrix(X, orc.FAMILY_ANISO_LAMBDA, [0.3, 2.0, 5.0, 1.5])).max() < 1e-13
+    r = api.Mixed_corr_vec([0.2, 0.7], X, 0.3, 2.0, 5.0, 1.5, engine=engine)
+    assert np.abs(r - orc.Mixed_corr_vec([0.2, 0.7], X, orc.FAMILY_ANISO_LAMBDA, [0.3, 2.0, 5.0, 1.5])).max() < 1e-13
+    Dn = designs["me_all_subdesigns"][3]
+    Cx = api.cross_corr_matrix(designs["me_initial14"], Dn, 4.0, engine=engine)
+    assert Cx.shape == (7, 14)
+    assert np.abs(Cx - orc.cross_corr_matrix(designs["me_initial14"], Dn, 4.0)).max() < 1e-13
+
+
+# ---------------------------------------------------------------- ME criteria
+def test_me_schur_golden_and_selection(engine, golden, designs):
+    D_old, pool = designs["me_initial14"], designs["me_all_subdesigns"]
+    nd, ld, st = engine.me_schur_batch(D_old, pool[:200], golden["me_params"])
+    assert np.all(st == 0)
+    assert rel_err(nd, golden["me_negdet_200"]).max() < 1e-9
+    assert np.abs(nd - golden["me_negdet_200"]).max() / np.abs(golden["me_negdet_200"]).max() < TOL
+    assert np.array_equal(nd.argmin(axis=0), golden["me_argmin_200"])          # bit-exact selection
+    assert np.allclose(ld, np.log(-nd), rtol=0, atol=1e-12)
+    bv, bi = engine.me_argmin(D_old, pool, golden["me_params"][:1])
+    assert int(bi[0]) == int(golden["me_argmin_full_prior"])
+    assert rel_err(bv[0], golden["me_negdet_full_prior"].min()) < 1e-9
+    # both code paths (specialised kernel / generic factor engine) select the same designs
+    os.environ["CCGP_ME_GENERIC"] = "1"
+    try:
+        nd_g, _, _ = engine.me_schur_batch(D_old, pool[:200], golden["me_params"])
+    finally:
+        os.environ.pop("CCGP_ME_GENERIC", None)
+    assert np.abs(nd_g - nd).max() / np.abs(nd).max() < 1e-12
+    assert np.array_equal(nd_g.argmin(axis=0), golden["me_argmin_200"])
+
+
+def test_entropy_first_batch(engine, golden, designs):
+    D_old, pool = designs["me_initial14"], designs["me_all_subdesigns"]
+    for q, want in zip(golden["me_params"], golden["entropy_initial14"]):
+        got = api.Entropy(D_old, *q, engine=engine)
+        assert abs(got - want) / abs(want) < 1e-9
+    d21 = np.stack([np.vstack([D_old, pool[c]]) for c in range(32)])
+    nd, _, _ = engine.me_schur_batch(None, d21, [[0.5, 1.0, 4.0]])
+    assert np.abs(nd[:, 0] - golden["entropy_pool21"]).max() / np.abs(golden["entropy_pool21"]).max() < 1e-9
+    a = api.Augmented_Mixed_Entropy(D_old, pool[5], 0.5, 1.0, 4.0, engine=engine)
+    assert rel_err(a, golden["me_negdet_200"][5, 0]) < 1e-9
+
+
+def test_me_full_pool_times_params_property(engine, designs):
+    """10^5 (pool x params) Schur determinants: det(R_all) = det(R_old) * det(Schur) for every pair,
+    and the per-row selection equals which.min of the returned matrix (first index on ties)."""
+    D_old, pool = workloads.me_pool()
+    params = workloads.me_params(100)
+    nd, ld, st = engine.me_schur_batch(D_old, pool, params)
+    assert nd.shape == (1000, 100) and np.all(st == 0) and np.all(nd < 0)
+    bv, bi = engine.me_argmin(D_old, pool, params)
+    assert np.array_equal(bi, nd.argmin(axis=0)) and np.array_equal(bv, nd.min(axis=0))
+    all21 = np.stack([np.vstack([D_old, pool[c]]) for c in range(1000)])
+    _, ld_all, _ = engine.me_schur_batch(None, all21, params[:5])
+    _, ld_old, _ = engine.me_schur_batch(None, D_old[None], params[:5])
+    assert np.abs(ld_all - (ld_old + ld[:, :5])).max() < 1e-8
+
+
+def test_batch_entropy_optim_improves_on_pool(engine, designs):
+    D_old, pool = workloads.me_pool()
+    res = api.Batch_Entropy_optim(D_old, 7, 2, 0.5, 1.0, 4.0, n_starts=3, rng=np.random.default_rng(1), engine=engine, maxiter=60)
+    assert res["Design"].shape == (7, 2) and np.all(np.abs(res["Design"]) <= 1.0)
+    assert res["log_entropy"] > 0
+    check = -orc.Augmented_Mixed_Entropy(D_old, res["Design"], 0.5, 1.0, 4.0, orc.mixed_R_old_inv(D_old, 0.5, 1.0, 4.0))
+    assert rel_err(res["log_entropy"], check) < 1e-8
+
+
+def test_subset_logdets(engine, golden):
+    pool, par = golden["sub_pool"], golden["sub_params"]
+    for m in (7, 21, 64):
+        got, st = engine.subset_logdet_batch(pool, golden["sub_idx_%d" % m], GAUSS_ANISO_LAMBDA, par)
+        assert np.all(st == 0)
+        assert np.abs(got - golden["sub_logdet_%d" % m]).max() < 1e-9
