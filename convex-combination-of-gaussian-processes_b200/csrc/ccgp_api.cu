@@ -223,7 +223,15 @@ extern "C" int ccgp_set_stream(ccgp_ctx* ctx, void* stream) {
     if (!ctx) return CCGP_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
-    ctx->stream = stream ? (cudaStream_t)stream : ctx->own_stream;
+    ctx->stream = (cudaStream_t)stream;   // NULL is the legacy default stream
+    return CCGP_OK;
+}
+
+extern "C" int ccgp_use_own_stream(ccgp_ctx* ctx) {
+    if (!ctx) return CCGP_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->stream = ctx->own_stream;
     return CCGP_OK;
 }
 

@@ -26,9 +26,11 @@
 namespace ccgp {
 
 constexpr int MAXD = 16;
-// a Cholesky pivot of the unit-diagonal R at or below 2 eps means kappa(R) > 1/(2 eps): the
-// analogue of base R's `solve` refusing rcond < .Machine$double.eps ([A]:448-449 -> NA)
-constexpr double PIVOT_MIN = 4.440892098500626e-16;
+// A Cholesky pivot of the unit-diagonal R at or below 64 eps means kappa(R) >~ 1e14, where
+// no digit of the likelihood survives: the analogue of base R's `solve` refusing
+// rcond < .Machine$double.eps ([A]:448-449 -> NA).  (Exactly duplicated design points give
+// pivots of a few eps of either sign; R refuses those through dgecon.)
+constexpr double PIVOT_MIN = 64 * 2.220446049250313e-16;
 constexpr double LOG2PI = 1.8378770664093454835606594728112;
 constexpr double LN2 = 0.69314718055994530941723212145818;
 

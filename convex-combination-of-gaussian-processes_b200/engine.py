@@ -59,8 +59,12 @@ class Engine:
         self._ck(self._lib.ccgp_sync(self._h))
 
     def set_stream(self, cuda_stream_ptr):
-        """Enqueue on the caller's stream (e.g. torch.cuda.current_stream().cuda_stream); None = own stream."""
-        self._ck(self._lib.ccgp_set_stream(self._h, cuda_stream_ptr))
+        """Enqueue on the caller's stream (e.g. torch.cuda.current_stream().cuda_stream, 0 = legacy
+        default stream); None = back to the engine's own stream."""
+        if cuda_stream_ptr is None:
+            self._ck(self._lib.ccgp_use_own_stream(self._h))
+        else:
+            self._ck(self._lib.ccgp_set_stream(self._h, C.c_void_p(int(cuda_stream_ptr))))
 
     @property
     def launch_count(self) -> int:

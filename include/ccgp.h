@@ -64,9 +64,11 @@ int ccgp_create(ccgp_ctx** ctx, int device);
 int ccgp_destroy(ccgp_ctx* ctx);
 const char* ccgp_last_error(const ccgp_ctx* ctx); /* ctx may be NULL: last create error */
 int ccgp_sync(ccgp_ctx* ctx);
-/* run on the caller's CUDA stream (a cudaStream_t; NULL = back to the context's own
- * stream) so the caller's events bracket the kernels */
+/* run on the caller's CUDA stream (a cudaStream_t; NULL = the legacy default stream)
+ * so the caller's events bracket the kernels; ccgp_use_own_stream goes back to the
+ * context's private non-blocking stream */
 int ccgp_set_stream(ccgp_ctx* ctx, void* stream);
+int ccgp_use_own_stream(ccgp_ctx* ctx);
 int ccgp_device(const ccgp_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int64_t ccgp_launch_count(const ccgp_ctx* ctx);
