@@ -26,7 +26,6 @@ struct ccgp_ctx {
     int n = 0, d = 0;
     double* d_X = nullptr;
     double* d_y = nullptr;
-    std::map<std::pair<int, int>, uint32_t*> ijtabs;  // (n, naug) -> decode table
     void* ws = nullptr;       // device workspace for the host-pointer entry points
     size_t ws_bytes = 0;
     void* ws2 = nullptr;      // small device workspace (params, reductions)
@@ -70,12 +69,12 @@ static int env_int(const char* name, int dflt) {
 
 // ------------------------------------------------------------------ variants
 typedef void (*factor_fn)(const FactorArgs);
-struct Variant { int team, tr, ks, minb; factor_fn fn_d0, fn_d2; };
+struct Variant { int team, tr, tc, minb; factor_fn fn_d0, fn_d2; };
 
 #define CCGP_VARIANTS(X)                                                                           \
-    X(32, 2, 1, 16) X(32, 4, 1, 16) X(64, 4, 1, 8) X(64, 4, 2, 8) X(128, 4, 2, 4) X(128, 4, 4, 4)     \
-    X(128, 8, 4, 4) X(256, 4, 4, 2) X(256, 8, 4, 2) X(64, 2, 2, 8) X(128, 2, 4, 4) X(256, 4, 8, 2)    \
-    X(128, 4, 1, 4) X(128, 4, 4, 5) X(64, 2, 1, 8) X(256, 2, 8, 2)
+    X(32, 2, 4, 16) X(32, 4, 4, 16) X(64, 2, 4, 8) X(64, 4, 4, 8) X(64, 4, 8, 8) X(128, 2, 4, 4)      \
+    X(128, 4, 4, 4) X(128, 4, 8, 4) X(128, 2, 8, 4) X(256, 2, 4, 2) X(256, 4, 4, 2) X(256, 4, 8, 2)   \
+    X(128, 2, 2, 4) X(64, 2, 8, 8) X(128, 8, 4, 4) X(256, 2, 8, 2)
 
 #define X(T, R, K, M) {T, R, K, M, factor_kernel<T, R, K, 0, M>, factor_kernel<T, R, K, 2, M>},
 static const Variant g_variants[] = {CCGP_VARIANTS(X)};
@@ -83,29 +82,11 @@ static const Variant g_variants[] = {CCGP_VARIANTS(X)};
 static const int g_num_variants = sizeof(g_variants) / sizeof(g_variants[0]);
 
 static int default_variant(const Layout& l) {
-    if (l.npad <= 24) return 0;    // 32 x TR2
-    if (l.npad <= 40) return 1;    // 32 x TR4
-    if (l.npad <= 72) return 9;    // 64 x TR2 x KS2
-    if (l.npad <= 136) return 5;   // 128 x TR4 x KS4
-    return 7;                      // 256 x TR4 x KS4
-}
-
-static int get_ijtab(ccgp_ctx* ctx, const Layout& l, const uint32_t** out) {
-    auto key = std::make_pair(l.n, l.naug);
-    auto it = ctx->ijtabs.find(key);
-    if (it != ctx->ijtabs.end()) { *out = it->second; return 0; }
-    std::vector<uint32_t> h((size_t)l.total);
-    size_t e = 0;
-    for (int J = 0; J < l.NJ; ++J)
-        for (int c = 0; c < 8; ++c)
-            for (int i = 8 * J; i < l.npad; ++i) h[e++] = (uint32_t)i | ((uint32_t)(8 * J + c) << 16);
-    uint32_t* dptr = nullptr;
-    CK(cudaMalloc(&dptr, h.size() * 4));
-    CK(cudaMemcpyAsync(dptr, h.data(), h.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    ctx->ijtabs[key] = dptr;
-    *out = dptr;
-    return 0;
+    if (l.npad <= 24) return 0;    // 32 threads, 2x4 tiles
+    if (l.npad <= 40) return 1;    // 32 threads, 4x4 tiles
+    if (l.npad <= 72) return 3;    // 64 threads, 4x4 tiles
+    if (l.npad <= 136) return 6;   // 128 threads, 4x4 tiles
+    return 10;                     // 256 threads, 4x4 tiles
 }
 
 static int ensure_ws(ccgp_ctx* ctx, size_t bytes) {
@@ -138,7 +119,6 @@ static int launch_factor(ccgp_ctx* ctx, FactorArgs& A) {
         return CCGP_ERR_UNSUPPORTED;
     }
     const Variant& var = g_variants[v];
-    // the row-slot passes need H/TR <= 32*G per pass only for efficiency; any size is correct
     factor_fn fn = (A.d == 2) ? var.fn_d2 : var.fn_d0;
     if (env_int("CCGP_NO_DT", 0)) fn = var.fn_d0;
     CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -148,7 +128,6 @@ static int launch_factor(ccgp_ctx* ctx, FactorArgs& A) {
     int64_t grid = (int64_t)nb * ctx->num_sm;
     if (grid > A.W) grid = A.W;
     if (grid < 1) return 0;
-    RC(get_ijtab(ctx, l, &A.ijtab));
     fn<<<(unsigned)grid, var.team, smem, ctx->stream>>>(A);
     CK(cudaGetLastError());
     ctx->launches++;
@@ -204,7 +183,6 @@ extern "C" int ccgp_destroy(ccgp_ctx* ctx) {
     if (!ctx) return CCGP_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (auto& kv : ctx->ijtabs) cudaFree(kv.second);
     if (ctx->d_X) cudaFree(ctx->d_X);
     if (ctx->d_y) cudaFree(ctx->d_y);
     if (ctx->ws) cudaFree(ctx->ws);
@@ -529,7 +507,6 @@ extern "C" int ccgp_rinv_batch(ccgp_ctx* ctx, int family, int scale, const doubl
     A.lay = l; A.d = ctx->d; A.design_mode = DESIGN_SHARED; A.X = ctx->d_X; A.y = ctx->d_y; A.n_designs = 1;
     A.cand = d_cand; A.ldc = B; A.n_params = B; A.family = family; A.logscale = scale; A.sigma2 = 1.0; A.W = B;
     A.out_mode = OUT_NLL;
-    RC(get_ijtab(ctx, l, &A.ijtab));
     P.out_rinv = d_rinv; P.out_beta = d_beta; P.status = d_status;
     auto fn = rinv_kernel<TEAM, 4, 4, 2>;
     CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -545,7 +522,7 @@ extern "C" int ccgp_rinv_batch(ccgp_ctx* ctx, int family, int scale, const doubl
 }
 
 // ------------------------------------------------------------------ predict
-template <int TEAM, int TR, int KS, int MR, int MINB>
+template <int TEAM, int TR, int TC, int MR, int MINB>
 static int launch_predict(ccgp_ctx* ctx, PredictArgs& P) {
     constexpr int TP = 4;
     const Layout& l = P.F.lay;
@@ -554,7 +531,7 @@ static int launch_predict(ccgp_ctx* ctx, PredictArgs& P) {
         snprintf(ctx->err, sizeof(ctx->err), "ccgp_predict: n=%d exceeds the shared-memory path", l.n);
         return CCGP_ERR_UNSUPPORTED;
     }
-    auto fn = predict_kernel<TEAM, TR, KS, 0, MR, TP, MINB>;
+    auto fn = predict_kernel<TEAM, TR, TC, 0, MR, TP, MINB>;
     CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int nb = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, TEAM, smem));
@@ -585,13 +562,11 @@ extern "C" int ccgp_predict_dev(ccgp_ctx* ctx, int family, const double* d_pars,
     A.d = ctx->d; A.design_mode = DESIGN_SHARED; A.X = ctx->d_X; A.y = ctx->d_y; A.n_designs = 1;
     A.cand = d_pars; A.ldc = ldp; A.n_params = S; A.family = family; A.logscale = 0; A.sigma2 = sigma2; A.W = S;
     A.out_mode = OUT_NLL;
-    int rc = get_ijtab(ctx, A.lay, &A.ijtab);
-    if (rc) return rc;
     P.Xnew = d_Xnew; P.T = T; P.candv = d_pars_vec; P.ldcv = ldpv; P.vec_family = vec_family;
     P.out_mean = d_mean; P.out_var = d_var; P.status = d_status;
     const int n = ctx->n;
-    if (n <= 32) return launch_predict<64, 2, 1, 1, 8>(ctx, P);
-    if (n <= 64) return launch_predict<128, 2, 4, 2, 4>(ctx, P);
+    if (n <= 32) return launch_predict<64, 2, 4, 1, 8>(ctx, P);
+    if (n <= 64) return launch_predict<128, 4, 4, 2, 4>(ctx, P);
     if (n <= 128) return launch_predict<128, 4, 4, 4, 4>(ctx, P);
     if (n <= 256) return launch_predict<256, 4, 4, 8, 2>(ctx, P);
     snprintf(ctx->err, sizeof(ctx->err), "ccgp_predict: n=%d > 256 not supported yet", n);

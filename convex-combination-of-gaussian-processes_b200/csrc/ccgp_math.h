@@ -30,6 +30,40 @@ CCGP_HD double ccgp_scale2(double v, int k) {
 #endif
 }
 
+#if defined(__CUDACC__)
+// Coefficients live in constant memory so each Horner step is one DFMA with a constant-bank
+// operand (64-bit immediates would cost two extra uniform moves per step).
+static __constant__ double c_dexp[16] = {
+    6755399441055744.0, 1.4426950408889634074, -6.93147180369123816490e-01, -1.90821492927058770002e-10,
+    2.5100424157005067e-08, 2.7620138719733994e-07, 2.7557268378684192e-06, 2.480152119021773e-05,
+    0.00019841269863105968, 0.0013888888917281794, 0.008333333333330051, 0.04166666666662399,
+    0.16666666666666669, 0.5000000000000001, 700.0, 0.0};
+
+// device version: branch-free, argument clamped at 700 (exp(-700) ~ 1e-304, no denormals)
+__device__ __forceinline__ double dexp_neg_dev(double s) {
+    s = fmin(s, c_dexp[14]);
+    double t = fma(-s, c_dexp[1], c_dexp[0]);
+    double kf = t - c_dexp[0];
+    double r = fma(kf, c_dexp[2], -s);
+    r = fma(kf, c_dexp[3], r);
+    double q = c_dexp[4];
+    q = fma(q, r, c_dexp[5]);
+    q = fma(q, r, c_dexp[6]);
+    q = fma(q, r, c_dexp[7]);
+    q = fma(q, r, c_dexp[8]);
+    q = fma(q, r, c_dexp[9]);
+    q = fma(q, r, c_dexp[10]);
+    q = fma(q, r, c_dexp[11]);
+    q = fma(q, r, c_dexp[12]);
+    q = fma(q, r, c_dexp[13]);
+    double r2 = r * r;
+    double e = fma(r2, q, r) + 1.0;
+    // t = MAGIC + k exactly, so k sits in the low word of t (two's complement)
+    int k = __double2loint(t);
+    return __hiloint2double(__double2hiint(e) + (k << 20), __double2loint(e));
+}
+#endif
+
 CCGP_HD double dexp_neg(double s) {
     const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52: rint() by add/sub
     double t = fma(-s, 1.4426950408889634074, MAGIC);

@@ -12,12 +12,22 @@
 //   z_y = L^-1 y and z_1 = L^-1 1, so the triangular solves are free.
 //   beta = z_1.z_y / z_1.z_1,  Q_R = |z_y - beta z_1|^2,  log det R = sum log piv.
 //
+// Schedule per panel J (3 team barriers):
+//   [A] every warp: K-loop  panel_J -= L[:, <8J] L[8J..8J+7, <8J]'.  Warps own disjoint
+//       row slots (no cross-warp reduction); when a warp has fewer than 32 tiles its lanes
+//       split K and the partial tiles are summed with xor-shuffles.
+//   [B] warp 0 factors the 8x8 diagonal block (lane r <-> row r, one shuffle + one rsqrt on
+//       the per-column critical chain) WHILE the other warps assemble the correlation
+//       entries of panel J+1 (2 exp per entry) -- the covariance build is the filler that
+//       hides the serial part.
+//   [C] one thread per remaining row: triangular solve against the diagonal block.
+//
 // Shared-memory layout of L ("block-column trapezoid"): block column J (8 wide)
 // stores rows 8J..npad-1 column-major with height H_J = npad-8J, block columns
 // back to back.  Every column start is 16-byte aligned so rows are read as
 // double2; a column of L is contiguous in its row index, so the K-loop row
 // loads of consecutive lanes are consecutive 16-byte words (conflict-free) and
-// the 8 panel-row values are warp-wide broadcasts.
+// the panel-row values are warp-wide broadcasts.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -96,7 +106,6 @@ struct FactorArgs {
     int mean_mode;
     double tau;
     int64_t W;            // work items: w -> design w % n_designs, parameter row w / n_designs
-    const uint32_t* ijtab;
     double* out0;         // NLL: nll          DET: log det (all pivots)
     double* out1;         // NLL: beta         DET: log det (tail pivots)
     double* out2;         // DET: -det(tail) (negated determinant, the ME criterion value)
@@ -159,69 +168,77 @@ __device__ inline void load_params(const FactorArgs& A, int64_t pi, Prm* prm) {
     prm->p = p;
 }
 
-// mixed correlation of points i and j of the staged design
-template <int DT>
-__device__ __forceinline__ double mixed_corr(const double* Xs, int npx, int d, int i, int j,
-                                             const double* wts, double rho, double a, double b) {
-    double s1 = 0.0;
-    if (DT > 0) {
-#pragma unroll
-        for (int k = 0; k < DT; ++k) {
-            double df = Xs[k * npx + i] - Xs[k * npx + j];
-            s1 = fma(wts[k] * df, df, s1);
-        }
-    } else {
-        for (int k = 0; k < d; ++k) {
-            double df = Xs[k * npx + i] - Xs[k * npx + j];
-            s1 = fma(wts[k] * df, df, s1);
-        }
-    }
-    double e1 = dexp_neg(s1);
-    double e2 = dexp_neg(rho * s1);
-    return fma(b, e2, a * e1);
-}
-
 struct FactorResult {  // valid in thread 0 of the team after factor_candidate()
     double mant_all, mant_tail;
     int es_all, es_tail;
     int bad;
 };
 
-// Build A into Ls and factor it in place.  All threads of the team call this.
-template <int TEAM, int TR, int KS, int DT>
+// ---- assemble the entries of panel J (rows 8J..npad-1, 8 columns) -----------------------
+// `gt`/`gsz`: index and size (threads, multiple of 32) of the group of threads doing the work.
+// Warps take columns, lanes take rows: the row coordinates are per-lane, the column's are
+// broadcast.  Every slot of the panel is written (zeros above the diagonal / in dead columns,
+// y' and 1' in the two extra rows).
+template <int DT>
+__device__ __forceinline__ void build_panel(const FactorArgs& A, double* Ls, const double* Xs, const double* ys,
+                                            const Prm* prm, int J, int gt, int gsz) {
+    const int n = A.lay.n, npad = A.lay.npad, naug = A.lay.naug, npx = A.lay.npx, d = A.d;
+    const int H = npad - 8 * J;
+    double* pan = Ls + blk_base(J, npad);
+    const int gw = gt >> 5, gnw = gsz >> 5, lane = gt & 31;
+    const double rho = prm->rho, a = prm->a, b = prm->b;
+    double wts[DT > 0 ? DT : 1];
+    if (DT > 0) {
+#pragma unroll
+        for (int k = 0; k < DT; ++k) wts[k] = prm->wts[k];
+    }
+    for (int r0 = lane; r0 < H; r0 += 32) {
+        const int i = 8 * J + r0;
+        const int ic = min(i, n - 1);
+        double xi[DT > 0 ? DT : 1];
+        if (DT > 0) {
+#pragma unroll
+            for (int k = 0; k < DT; ++k) xi[k] = Xs[k * npx + ic];
+        }
+        for (int c = gw; c < 8; c += gnw) {
+            const int j = 8 * J + c;
+            const int jc = min(j, n - 1);
+            double s1 = 0.0;
+            if (DT > 0) {
+#pragma unroll
+                for (int k = 0; k < DT; ++k) {
+                    double df = xi[k] - Xs[k * npx + jc];
+                    s1 = fma(wts[k] * df, df, s1);
+                }
+            } else {
+                for (int k = 0; k < d; ++k) {
+                    double df = Xs[k * npx + ic] - Xs[k * npx + jc];
+                    s1 = fma(prm->wts[k] * df, df, s1);
+                }
+            }
+            double v = fma(b, dexp_neg_dev(rho * s1), a * dexp_neg_dev(s1));
+            if (i >= n) v = (naug && i == n) ? ys[jc] : ((naug && i == n + 1) ? 1.0 : 0.0);
+            if (i == j) v = 1.0;
+            if (i < j || j >= n) v = 0.0;
+            pan[c * H + r0] = v;
+        }
+    }
+}
+
+// Build A panel by panel and factor it in place.  All threads of the team call this.
+template <int TEAM, int TR, int TC, int DT>
 __device__ __forceinline__ FactorResult factor_candidate(const FactorArgs& A, double* Ls, const double* Xs,
                                                          const double* ys, double* rinv_s, const Prm* prm) {
     static_assert(TR == 2 || TR == 4 || TR == 8, "TR");
-    static_assert((TEAM / 32) % KS == 0, "KS must divide the warp count");
-    constexpr int G = (TEAM / 32) / KS;
+    static_assert(TC == 2 || TC == 4 || TC == 8, "TC");
+    constexpr int W = TEAM / 32;
+    constexpr int CG = 8 / TC;
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    const int ks = warp % KS;
-    const int g = warp / KS;
-    const int n = A.lay.n, npad = A.lay.npad, NJ = A.lay.NJ, naug = A.lay.naug, npx = A.lay.npx, d = A.d;
+    const int n = A.lay.n, npad = A.lay.npad, NJ = A.lay.NJ;
 
-    // ---- build: every stored slot (i,j) of the trapezoid ---------------------
-    {
-        double wts[DT > 0 ? DT : 1];
-        if (DT > 0) {
-#pragma unroll
-            for (int k = 0; k < DT; ++k) wts[k] = prm->wts[k];
-        }
-        const double rho = prm->rho, a = prm->a, b = prm->b;
-        for (int e = tid; e < A.lay.total; e += TEAM) {
-            uint32_t ij = __ldg(A.ijtab + e);
-            int i = ij & 0xffff, j = ij >> 16;
-            double v;
-            if (j >= n || i < j) v = 0.0;
-            else if (i == j) v = 1.0;
-            else if (i < n) v = mixed_corr<DT>(Xs, npx, d, i, j, DT > 0 ? wts : prm->wts, rho, a, b);
-            else if (naug && i == n) v = ys[j];
-            else if (naug && i == n + 1) v = 1.0;
-            else v = 0.0;
-            Ls[e] = v;
-        }
-    }
+    build_panel<DT>(A, Ls, Xs, ys, prm, 0, tid, TEAM);
     team_sync<TEAM>();
 
     FactorResult res;
@@ -230,66 +247,82 @@ __device__ __forceinline__ FactorResult factor_candidate(const FactorArgs& A, do
     for (int J = 0; J < NJ; ++J) {
         const int H = npad - 8 * J;
         const int pbase = blk_base(J, npad);
-        // ---- left-looking update of panel J with block columns < J -------------
+        // ---- [A] left-looking update of panel J with block columns < J ---------------------
         if (J > 0) {
-            const int Q = H / TR;
-            for (int q0 = 0; q0 < Q; q0 += G * 32) {
-                const int q = q0 + g * 32 + lane;
-                const bool act = (q < Q) && (ks < J);
-                double acc[TR][8];
+            const int Q = H / TR;                 // row slots
+            const int T = Q * CG;                 // tiles of the panel
+            const int Tw = (T + W - 1) / W;       // tiles per warp (blocked)
+            for (int t0 = 0; t0 < Tw; t0 += 32) {
+                const int Tc = min(Tw - t0, 32);
+                int lg = 0;
+                while ((1 << lg) < Tc) ++lg;
+                int lgS = 5 - lg;                                   // in-warp K-split = 2^lgS
+                while (lgS > 0 && ((8 * J) >> lgS) < 4) --lgS;      // keep >= 4 k-steps per lane
+                const int Tp = 32 >> lgS;
+                const int S = 1 << lgS;
+                const int tl = lane & (Tp - 1), s = lane / Tp;
+                const int t = warp * Tw + t0 + tl;
+                const bool act = (tl < Tc) && (t < T);
+                const int q = act ? t / CG : 0, cg = act ? t % CG : 0;
+                double acc[TR][TC];
 #pragma unroll
                 for (int r = 0; r < TR; ++r)
 #pragma unroll
-                    for (int cc = 0; cc < 8; ++cc) acc[r][cc] = 0.0;
+                    for (int cc = 0; cc < TC; ++cc) acc[r][cc] = 0.0;
                 if (act) {
-                    for (int J2 = ks; J2 < J; J2 += KS) {
+#pragma unroll 2
+                    for (int k = s; k < 8 * J; k += S) {
+                        const int J2 = k >> 3, c = k & 7;
                         const int H2 = npad - 8 * J2;
-                        const double* colp = Ls + blk_base(J2, npad) - 8 * J2 + 8 * J;
+                        const double* cp = Ls + blk_base(J2, npad) - 8 * J2 + c * H2 + 8 * J;   // cp[r] = L(8J+r, k)
+                        double lc[TC];
 #pragma unroll
-                        for (int c = 0; c < 8; ++c) {
-                            const double* cp = colp + c * H2;
-                            double2 l0 = ld2(cp), l1 = ld2(cp + 2), l2 = ld2(cp + 4), l3 = ld2(cp + 6);
-                            double lc[8] = {l0.x, l0.y, l1.x, l1.y, l2.x, l2.y, l3.x, l3.y};
+                        for (int cc = 0; cc < TC; cc += 2) {
+                            double2 v = ld2(cp + TC * cg + cc);
+                            lc[cc] = v.x; lc[cc + 1] = v.y;
+                        }
 #pragma unroll
-                            for (int m = 0; m < TR / 2; ++m) {
-                                double2 lr = ld2(cp + 2 * (q + Q * m));
+                        for (int m = 0; m < TR / 2; ++m) {
+                            double2 lr = ld2(cp + 2 * (q + Q * m));
 #pragma unroll
-                                for (int cc = 0; cc < 8; ++cc) {
-                                    acc[2 * m][cc] = fma(-lr.x, lc[cc], acc[2 * m][cc]);
-                                    acc[2 * m + 1][cc] = fma(-lr.y, lc[cc], acc[2 * m + 1][cc]);
-                                }
+                            for (int cc = 0; cc < TC; ++cc) {
+                                acc[2 * m][cc] = fma(-lr.x, lc[cc], acc[2 * m][cc]);
+                                acc[2 * m + 1][cc] = fma(-lr.y, lc[cc], acc[2 * m + 1][cc]);
                             }
                         }
                     }
                 }
-                // deterministic reduction of the KS partial sums into the panel
+                for (int o = Tp; o < 32; o <<= 1) {
 #pragma unroll
-                for (int r = 0; r < KS; ++r) {
-                    if (act && ks == r) {
+                    for (int r = 0; r < TR; ++r)
 #pragma unroll
-                        for (int m = 0; m < TR / 2; ++m)
+                        for (int cc = 0; cc < TC; ++cc) acc[r][cc] += __shfl_xor_sync(0xffffffffu, acc[r][cc], o);
+                }
+                if (act && s == 0) {
 #pragma unroll
-                            for (int cc = 0; cc < 8; ++cc) {
-                                double2* dst = reinterpret_cast<double2*>(Ls + pbase + cc * H + 2 * (q + Q * m));
-                                double2 v = *dst;
-                                v.x += acc[2 * m][cc];
-                                v.y += acc[2 * m + 1][cc];
-                                *dst = v;
-                            }
-                    }
-                    team_sync<TEAM>();
+                    for (int m = 0; m < TR / 2; ++m)
+#pragma unroll
+                        for (int cc = 0; cc < TC; ++cc) {
+                            double2* dst = reinterpret_cast<double2*>(Ls + pbase + (TC * cg + cc) * H + 2 * (q + Q * m));
+                            double2 v = *dst;
+                            v.x += acc[2 * m][cc];
+                            v.y += acc[2 * m + 1][cc];
+                            *dst = v;
+                        }
                 }
             }
+            team_sync<TEAM>();
         }
-        // ---- F1: factor the 8x8 diagonal block (warp 0; lane r <-> row 8J+r) ----
+        // ---- [B] warp 0: 8x8 diagonal block; other warps: assemble panel J+1 ---------------
         if (warp == 0) {
             const int r = lane & 7;
             double a8[8];
 #pragma unroll
             for (int c = 0; c < 8; ++c) a8[c] = Ls[pbase + c * H + r];
+            double dg = Ls[pbase + r * H + r];      // this row's diagonal entry, updated every step
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
-                const double piv = __shfl_sync(0xffffffffu, a8[c], c);
+                const double piv = __shfl_sync(0xffffffffu, dg, c);
                 const int j = 8 * J + c;
                 double ri = 0.0;
                 if (j < n) {
@@ -298,8 +331,10 @@ __device__ __forceinline__ FactorResult factor_candidate(const FactorArgs& A, do
                     prod_accum(res.mant_all, res.es_all, piv);
                     if (j >= A.tail0) prod_accum(res.mant_tail, res.es_tail, piv);
                 }
-                const double l = (r == c) ? piv * ri : a8[c] * ri;
+                double l = a8[c] * ri;
+                if (r == c) l = piv * ri;
                 a8[c] = l;
+                if (r > c) dg = fma(-l, l, dg);
 #pragma unroll
                 for (int c2 = c + 1; c2 < 8; ++c2) {
                     const double lc2 = __shfl_sync(0xffffffffu, l, c2);
@@ -313,8 +348,12 @@ __device__ __forceinline__ FactorResult factor_candidate(const FactorArgs& A, do
                     if (c <= r) Ls[pbase + c * H + r] = a8[c];
             }
         }
+        if (J + 1 < NJ) {
+            if (W == 1) build_panel<DT>(A, Ls, Xs, ys, prm, J + 1, tid, TEAM);
+            else if (warp > 0) build_panel<DT>(A, Ls, Xs, ys, prm, J + 1, tid - 32, TEAM - 32);
+        }
         team_sync<TEAM>();
-        // ---- F2: rows below the diagonal block, one thread per row -------------
+        // ---- [C] rows below the diagonal block, one thread per row ---------------------------
         if (H > 8) {
             double ljj[28];
             double ri[8];
@@ -391,7 +430,7 @@ __device__ __forceinline__ void stage_design(const FactorArgs& A, int64_t dsg, d
     }
 }
 
-template <int TEAM, int TR, int KS, int DT, int MINB>
+template <int TEAM, int TR, int TC, int DT, int MINB>
 __global__ void __launch_bounds__(TEAM, MINB) factor_kernel(const FactorArgs A) {
     extern __shared__ __align__(16) double smem[];
     const Layout& lay = A.lay;
@@ -420,7 +459,7 @@ __global__ void __launch_bounds__(TEAM, MINB) factor_kernel(const FactorArgs A) 
         if (A.design_mode != DESIGN_SHARED) stage_design<TEAM>(A, dsg, Xs);
         team_sync<TEAM>();
 
-        FactorResult res = factor_candidate<TEAM, TR, KS, DT>(A, Ls, Xs, ys, rinv_s, prm);
+        FactorResult res = factor_candidate<TEAM, TR, TC, DT>(A, Ls, Xs, ys, rinv_s, prm);
 
         if (A.out_mode == OUT_NLL) {
             double s11 = 0.0, s1y = 0.0;

@@ -40,7 +40,7 @@ inline size_t predict_smem_bytes(const Layout& l, int d) {
     return smem_bytes(l, d) + (size_t)(3 * l.npad + (TEAM / 32) * TP * l.npad) * 8 + sizeof(Prm) + 16 + MAXD * 8 * (TEAM / 32) * TP;
 }
 
-template <int TEAM, int TR, int KS, int DT, int MR, int TP, int MINB>
+template <int TEAM, int TR, int TC, int DT, int MR, int TP, int MINB>
 __global__ void __launch_bounds__(TEAM, MINB) predict_kernel(const PredictArgs P) {
     extern __shared__ __align__(16) double smem[];
     const FactorArgs& A = P.F;
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(TEAM, MINB) predict_kernel(const PredictArgs P
             }
         }
         __syncthreads();
-        FactorResult res = factor_candidate<TEAM, TR, KS, DT>(A, Ls, Xs, ys, rinv_s, prm);
+        FactorResult res = factor_candidate<TEAM, TR, TC, DT>(A, Ls, Xs, ys, rinv_s, prm);
         if (tid == 0) red[62] = res.bad ? 1.0 : 0.0;
 
         double s11 = 0.0, s1y = 0.0;
@@ -103,8 +103,7 @@ __global__ void __launch_bounds__(TEAM, MINB) predict_kernel(const PredictArgs P
         const bool bad = red[62] != 0.0;
         if (tid == 0 && P.status) P.status[s] = bad ? 1 : 0;
 
-        double* myrv = rv + warp * TP * npad;
-        double* myxn = xn + warp * TP * MAXD;
+            double* myxn = xn + warp * TP * MAXD;
         const int64_t ngroups = (P.T + TP - 1) / TP;
         for (int64_t tg = warp; tg < ngroups; tg += TEAM / 32) {
             const int64_t t0 = tg * TP;
@@ -193,7 +192,7 @@ inline size_t rinv_smem_bytes(const Layout& l, int d) {
 }
 
 // One CTA per candidate; warp w produces columns t = w, w+W, ... of R^-1.
-template <int TEAM, int TR, int KS, int MINB>
+template <int TEAM, int TR, int TC, int MINB>
 __global__ void __launch_bounds__(TEAM, MINB) rinv_kernel(const RinvArgs P) {
     extern __shared__ __align__(16) double smem[];
     const FactorArgs& A = P.F;
@@ -220,7 +219,7 @@ __global__ void __launch_bounds__(TEAM, MINB) rinv_kernel(const RinvArgs P) {
         __syncthreads();
         if (tid == 0) load_params(A, s, prm);
         __syncthreads();
-        FactorResult res = factor_candidate<TEAM, TR, KS, 0>(A, Ls, Xs, ys, rinv_s, prm);
+        FactorResult res = factor_candidate<TEAM, TR, TC, 0>(A, Ls, Xs, ys, rinv_s, prm);
         if (tid == 0) red[62] = res.bad ? 1.0 : 0.0;
         double s11 = 0.0, s1y = 0.0;
         for (int k = tid; k < n; k += TEAM) {
