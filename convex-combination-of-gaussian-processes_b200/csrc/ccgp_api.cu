@@ -26,6 +26,7 @@ struct ccgp_ctx {
     int n = 0, d = 0;
     double* d_X = nullptr;
     double* d_y = nullptr;
+    double span2[MAXD] = {0};   // squared coordinate ranges of the shared design
     void* ws = nullptr;       // device workspace for the host-pointer entry points
     size_t ws_bytes = 0;
     void* ws2 = nullptr;      // small device workspace (params, reductions)
@@ -34,6 +35,7 @@ struct ccgp_ctx {
     int64_t launches = 0;
     int last_team = 0, last_smem = 0, last_ctas = 0, last_variant = -1;
     BigCholWorkspace big;
+    long long* dbg = nullptr;  // phase-timing buffer (debug)
 };
 
 static char g_create_err[512] = "";
@@ -125,9 +127,11 @@ static int launch_factor(ccgp_ctx* ctx, FactorArgs& A) {
     int nb = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, var.team, smem));
     if (nb < 1) { snprintf(ctx->err, sizeof(ctx->err), "kernel variant %d does not fit", v); return CCGP_ERR_UNSUPPORTED; }
+    { int cap = env_int("CCGP_CTAS_PER_SM", 0); if (cap > 0 && cap < nb) nb = cap; }
     int64_t grid = (int64_t)nb * ctx->num_sm;
     if (grid > A.W) grid = A.W;
     if (grid < 1) return 0;
+    A.dbg = ctx->dbg;
     fn<<<(unsigned)grid, var.team, smem, ctx->stream>>>(A);
     CK(cudaGetLastError());
     ctx->launches++;
@@ -283,6 +287,16 @@ extern "C" int ccgp_set_design(ccgp_ctx* ctx, const double* X, int n, int d, con
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->n = n;
     ctx->d = d;
+    for (int k = 0; k < d; ++k) {
+        double lo = X[(size_t)k * n], hi = lo;
+        for (int i = 1; i < n; ++i) {
+            double v = X[(size_t)k * n + i];
+            lo = v < lo ? v : lo;
+            hi = v > hi ? v : hi;
+        }
+        ctx->span2[k] = (hi - lo) * (hi - lo);
+        if (!(ctx->span2[k] == ctx->span2[k])) ctx->span2[k] = 1e300;   // NaN coordinates: take the safe path
+    }
     return CCGP_OK;
 }
 
@@ -318,7 +332,7 @@ extern "C" int ccgp_nll_batch_dev(ccgp_ctx* ctx, int family, int scale, const do
     memset(&A, 0, sizeof(A));
     A.lay = l;
     A.d = ctx->d;
-    A.design_mode = DESIGN_SHARED;
+    A.design_mode = DESIGN_SHARED; memcpy(A.span2, ctx->span2, sizeof(A.span2));
     A.X = ctx->d_X;
     A.y = ctx->d_y;
     A.n_designs = 1;
@@ -504,7 +518,7 @@ extern "C" int ccgp_rinv_batch(ccgp_ctx* ctx, int family, int scale, const doubl
     RinvArgs P;
     memset(&P, 0, sizeof(P));
     FactorArgs& A = P.F;
-    A.lay = l; A.d = ctx->d; A.design_mode = DESIGN_SHARED; A.X = ctx->d_X; A.y = ctx->d_y; A.n_designs = 1;
+    A.lay = l; A.d = ctx->d; A.design_mode = DESIGN_SHARED; memcpy(A.span2, ctx->span2, sizeof(A.span2)); A.X = ctx->d_X; A.y = ctx->d_y; A.n_designs = 1;
     A.cand = d_cand; A.ldc = B; A.n_params = B; A.family = family; A.logscale = scale; A.sigma2 = 1.0; A.W = B;
     A.out_mode = OUT_NLL;
     P.out_rinv = d_rinv; P.out_beta = d_beta; P.status = d_status;
@@ -559,7 +573,7 @@ extern "C" int ccgp_predict_dev(ccgp_ctx* ctx, int family, const double* d_pars,
     memset(&P, 0, sizeof(P));
     FactorArgs& A = P.F;
     A.lay = make_layout(ctx->n, 2);
-    A.d = ctx->d; A.design_mode = DESIGN_SHARED; A.X = ctx->d_X; A.y = ctx->d_y; A.n_designs = 1;
+    A.d = ctx->d; A.design_mode = DESIGN_SHARED; memcpy(A.span2, ctx->span2, sizeof(A.span2)); A.X = ctx->d_X; A.y = ctx->d_y; A.n_designs = 1;
     A.cand = d_pars; A.ldc = ldp; A.n_params = S; A.family = family; A.logscale = 0; A.sigma2 = sigma2; A.W = S;
     A.out_mode = OUT_NLL;
     P.Xnew = d_Xnew; P.T = T; P.candv = d_pars_vec; P.ldcv = ldpv; P.vec_family = vec_family;
@@ -628,7 +642,7 @@ extern "C" int ccgp_me_schur_batch_dev(ccgp_ctx* ctx, const double* d_D_old, int
     memset(&A, 0, sizeof(A));
     A.lay = make_layout(n_old + n_new, 0);
     A.d = d;
-    A.design_mode = DESIGN_OLD_PLUS_NEW;
+    A.design_mode = DESIGN_OLD_PLUS_NEW; A.force_clamp = 1;
     A.X = d_D_old; A.Dnew = d_D_new; A.n_old = n_old; A.tail0 = n_old;
     A.n_designs = C;
     A.cand = d_params; A.ldc = ldq; A.n_params = P; A.family = FAM_ISO; A.logscale = 0; A.sigma2 = 1.0;
@@ -714,7 +728,7 @@ extern "C" int ccgp_subset_logdet_batch_dev(ccgp_ctx* ctx, const double* d_pool,
     memset(&A, 0, sizeof(A));
     A.lay = make_layout(m, 0);
     A.d = d;
-    A.design_mode = DESIGN_GATHER;
+    A.design_mode = DESIGN_GATHER; A.force_clamp = 1;
     A.X = d_pool; A.ldpool = N; A.idx = d_idx; A.ldi = ldi; A.tail0 = 0;
     A.n_designs = C;
     A.cand = d_par; A.ldc = 1; A.n_params = 1; A.family = family; A.logscale = 0; A.sigma2 = 1.0;
@@ -790,7 +804,7 @@ extern "C" int ccgp_mixed_corr(ccgp_ctx* ctx, int family, const double* params, 
     if (!same) CK(cudaMemcpyAsync(d_B, B, (size_t)nb * d * 8, cudaMemcpyHostToDevice, ctx->stream));
     FactorArgs F;
     memset(&F, 0, sizeof(F));
-    F.d = d; F.cand = d_par; F.ldc = 1; F.n_params = 1; F.family = family; F.logscale = 0; F.sigma2 = 1.0;
+    F.force_clamp = 1; F.d = d; F.cand = d_par; F.ldc = 1; F.n_params = 1; F.family = family; F.logscale = 0; F.sigma2 = 1.0;
     int64_t tot = (int64_t)na * nb;
     int grid = (int)std::min<int64_t>((tot + 255) / 256, (int64_t)ctx->num_sm * 8);
     mixed_corr_kernel<<<grid, 256, 0, ctx->stream>>>(F, d_A, na, d_B, nb, d_out, same);
@@ -798,5 +812,21 @@ extern "C" int ccgp_mixed_corr(ccgp_ctx* ctx, int family, const double* params, 
     ctx->launches++;
     CK(cudaMemcpyAsync(out, d_out, (size_t)na * nb * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    return CCGP_OK;
+}
+
+// ---- debug: per-phase clock counters of the factor kernel (block 0, warps 0 and 1) --------
+extern "C" int ccgp_debug_phase_timing(ccgp_ctx* ctx, int enable, long long* out32) {
+    if (!ctx) return CCGP_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (out32 && ctx->dbg) CK(cudaMemcpy(out32, ctx->dbg, 32 * sizeof(long long), cudaMemcpyDeviceToHost));
+    if (enable) {
+        if (!ctx->dbg) CK(cudaMalloc(&ctx->dbg, 32 * sizeof(long long)));
+        CK(cudaMemset(ctx->dbg, 0, 32 * sizeof(long long)));
+    } else if (ctx->dbg) {
+        CK(cudaFree(ctx->dbg));
+        ctx->dbg = nullptr;
+    }
     return CCGP_OK;
 }

@@ -39,9 +39,12 @@ static __constant__ double c_dexp[16] = {
     0.00019841269863105968, 0.0013888888917281794, 0.008333333333330051, 0.04166666666662399,
     0.16666666666666669, 0.5000000000000001, 700.0, 0.0};
 
-// device version: branch-free, argument clamped at 700 (exp(-700) ~ 1e-304, no denormals)
+// device version, branch-free.  CLAMP=false: the caller guarantees s < 1e8 (checked once per
+// candidate from the parameter row and the design's bounding box), so only the power-of-two
+// exponent is clamped (one integer max); CLAMP=true clamps the argument itself at 700.
+template <bool CLAMP>
 __device__ __forceinline__ double dexp_neg_dev(double s) {
-    s = fmin(s, c_dexp[14]);
+    if (CLAMP) s = fmin(s, c_dexp[14]);
     double t = fma(-s, c_dexp[1], c_dexp[0]);
     double kf = t - c_dexp[0];
     double r = fma(kf, c_dexp[2], -s);
@@ -60,6 +63,7 @@ __device__ __forceinline__ double dexp_neg_dev(double s) {
     double e = fma(r2, q, r) + 1.0;
     // t = MAGIC + k exactly, so k sits in the low word of t (two's complement)
     int k = __double2loint(t);
+    if (!CLAMP) k = max(k, -1010);
     return __hiloint2double(__double2hiint(e) + (k << 20), __double2loint(e));
 }
 #endif

@@ -31,6 +31,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <type_traits>
 #include "ccgp_math.h"
 
 namespace ccgp {
@@ -54,6 +55,8 @@ struct Prm {  // per-candidate parameters, one copy in shared memory
     double a, b;       // p^2/w, (1-p)^2/w
     double c;          // w * sigma2
     double p;
+    int clamp;         // 1: exponents may exceed 1e8 -> use the argument-clamping exp
+    int pad_;
 };
 
 struct Layout {
@@ -106,12 +109,23 @@ struct FactorArgs {
     int mean_mode;
     double tau;
     int64_t W;            // work items: w -> design w % n_designs, parameter row w / n_designs
+    double span2[MAXD];   // squared coordinate ranges of the design (bounds the exponents)
+    int force_clamp;      // 1 when span2 is unknown (per-candidate designs)
+    long long* dbg;       // optional phase-timing buffer (tools/phase_timing.py); NULL in production
     double* out0;         // NLL: nll          DET: log det (all pivots)
     double* out1;         // NLL: beta         DET: log det (tail pivots)
     double* out2;         // DET: -det(tail) (negated determinant, the ME criterion value)
     int32_t* status;
     int out_mode;
 };
+
+// phase timing (debug): block 0, lane 0 of warps 0 and 1 accumulate clock deltas per phase:
+// slot = warp*16 + phase*2 + {0: work until the barrier, 1: wait inside the barrier}
+#define CCGP_T0() long long t_ph = (A.dbg && blockIdx.x == 0) ? clock64() : 0
+#define CCGP_TW(ph) do { if (A.dbg && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (threadIdx.x >> 5) < 2) { \
+        long long t1_ = clock64(); A.dbg[(threadIdx.x >> 5) * 16 + (ph) * 2] += t1_ - t_ph; t_ph = t1_; } } while (0)
+#define CCGP_TB(ph) do { if (A.dbg && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (threadIdx.x >> 5) < 2) { \
+        long long t1_ = clock64(); A.dbg[(threadIdx.x >> 5) * 16 + (ph) * 2 + 1] += t1_ - t_ph; t_ph = t1_; } } while (0)
 
 template <int TEAM>
 __device__ __forceinline__ void team_sync() {
@@ -166,6 +180,10 @@ __device__ inline void load_params(const FactorArgs& A, int64_t pi, Prm* prm) {
     prm->b = (1.0 - p) * (1.0 - p) / w;
     prm->c = w * A.sigma2;
     prm->p = p;
+    double smax = 0.0;
+    for (int k = 0; k < d; ++k) smax += prm->wts[k] * A.span2[k];
+    smax *= fmax(rho, 1.0);
+    prm->clamp = (A.force_clamp || !(smax < 1e8)) ? 1 : 0;
 }
 
 struct FactorResult {  // valid in thread 0 of the team after factor_candidate()
@@ -178,8 +196,9 @@ struct FactorResult {  // valid in thread 0 of the team after factor_candidate()
 // `gt`/`gsz`: index and size (threads, multiple of 32) of the group of threads doing the work.
 // Warps take columns, lanes take rows: the row coordinates are per-lane, the column's are
 // broadcast.  Every slot of the panel is written (zeros above the diagonal / in dead columns,
-// y' and 1' in the two extra rows).
-template <int DT>
+// y' and 1' in the two extra rows).  Rows >= n and the 8x8 diagonal corner are fixed up on
+// rarely-taken branches so the common entry costs the two exponentials and little else.
+template <int DT, bool CLAMP>
 __device__ __forceinline__ void build_panel(const FactorArgs& A, double* Ls, const double* Xs, const double* ys,
                                             const Prm* prm, int J, int gt, int gsz) {
     const int n = A.lay.n, npad = A.lay.npad, naug = A.lay.naug, npx = A.lay.npx, d = A.d;
@@ -192,35 +211,47 @@ __device__ __forceinline__ void build_panel(const FactorArgs& A, double* Ls, con
 #pragma unroll
         for (int k = 0; k < DT; ++k) wts[k] = prm->wts[k];
     }
-    for (int r0 = lane; r0 < H; r0 += 32) {
-        const int i = 8 * J + r0;
-        const int ic = min(i, n - 1);
-        double xi[DT > 0 ? DT : 1];
+    for (int c = gw; c < 8; c += gnw) {
+        const int j = 8 * J + c;
+        double* col = pan + c * H;
+        if (j >= n) {                                    // dead column (warp-uniform)
+            for (int r0 = lane; r0 < H; r0 += 32) col[r0] = 0.0;
+            continue;
+        }
+        double xj[DT > 0 ? DT : 1];
         if (DT > 0) {
 #pragma unroll
-            for (int k = 0; k < DT; ++k) xi[k] = Xs[k * npx + ic];
+            for (int k = 0; k < DT; ++k) xj[k] = Xs[k * npx + j];
         }
-        for (int c = gw; c < 8; c += gnw) {
-            const int j = 8 * J + c;
-            const int jc = min(j, n - 1);
-            double s1 = 0.0;
+        // two rows per iteration (passes u and u + half) keep four exponentials in flight
+        const int P = (H + 31) >> 5, half = (P + 1) >> 1;
+        for (int u = 0; u < half; ++u) {
+            const int ra = lane + 32 * u, rb = ra + 32 * half;
+            const int ia = 8 * J + ra, ib = 8 * J + rb;
+            const int ica = min(ia, n - 1), icb = min(ib, n - 1);     // rows >= n are fixed up below
+            double s1a = 0.0, s1b = 0.0;
             if (DT > 0) {
 #pragma unroll
                 for (int k = 0; k < DT; ++k) {
-                    double df = xi[k] - Xs[k * npx + jc];
-                    s1 = fma(wts[k] * df, df, s1);
+                    double da = Xs[k * npx + ica] - xj[k], db = Xs[k * npx + icb] - xj[k];
+                    s1a = fma(wts[k] * da, da, s1a);
+                    s1b = fma(wts[k] * db, db, s1b);
                 }
             } else {
                 for (int k = 0; k < d; ++k) {
-                    double df = Xs[k * npx + ic] - Xs[k * npx + jc];
-                    s1 = fma(prm->wts[k] * df, df, s1);
+                    const double xjk = Xs[k * npx + j], wk = prm->wts[k];
+                    double da = Xs[k * npx + ica] - xjk, db = Xs[k * npx + icb] - xjk;
+                    s1a = fma(wk * da, da, s1a);
+                    s1b = fma(wk * db, db, s1b);
                 }
             }
-            double v = fma(b, dexp_neg_dev(rho * s1), a * dexp_neg_dev(s1));
-            if (i >= n) v = (naug && i == n) ? ys[jc] : ((naug && i == n + 1) ? 1.0 : 0.0);
-            if (i == j) v = 1.0;
-            if (i < j || j >= n) v = 0.0;
-            pan[c * H + r0] = v;
+            double va = fma(b, dexp_neg_dev<CLAMP>(rho * s1a), a * dexp_neg_dev<CLAMP>(s1a));
+            double vb = fma(b, dexp_neg_dev<CLAMP>(rho * s1b), a * dexp_neg_dev<CLAMP>(s1b));
+            if (ra <= c) va = (ra == c) ? 1.0 : 0.0;   // diagonal corner: unit diagonal, unused upper part
+            if (ia >= n) va = (naug && ia == n) ? ys[j] : ((naug && ia == n + 1) ? 1.0 : 0.0);
+            if (ib >= n) vb = (naug && ib == n) ? ys[j] : ((naug && ib == n + 1) ? 1.0 : 0.0);
+            if (ra < H) col[ra] = va;
+            if (rb < H && u + half < P) col[rb] = vb;
         }
     }
 }
@@ -238,8 +269,13 @@ __device__ __forceinline__ FactorResult factor_candidate(const FactorArgs& A, do
     const int warp = tid >> 5;
     const int n = A.lay.n, npad = A.lay.npad, NJ = A.lay.NJ;
 
-    build_panel<DT>(A, Ls, Xs, ys, prm, 0, tid, TEAM);
+    const bool clampx = prm->clamp != 0;
+    CCGP_T0();
+    if (clampx) build_panel<DT, true>(A, Ls, Xs, ys, prm, 0, tid, TEAM);
+    else build_panel<DT, false>(A, Ls, Xs, ys, prm, 0, tid, TEAM);
+    CCGP_TW(0);
     team_sync<TEAM>();
+    CCGP_TB(0);
 
     FactorResult res;
     res.mant_all = 1.0; res.mant_tail = 1.0; res.es_all = 0; res.es_tail = 0; res.bad = 0;
@@ -254,8 +290,7 @@ __device__ __forceinline__ FactorResult factor_candidate(const FactorArgs& A, do
             const int Tw = (T + W - 1) / W;       // tiles per warp (blocked)
             for (int t0 = 0; t0 < Tw; t0 += 32) {
                 const int Tc = min(Tw - t0, 32);
-                int lg = 0;
-                while ((1 << lg) < Tc) ++lg;
+                const int lg = (Tc <= 1) ? 0 : 32 - __clz(Tc - 1);      // ceil(log2(Tc))
                 int lgS = 5 - lg;                                   // in-warp K-split = 2^lgS
                 while (lgS > 0 && ((8 * J) >> lgS) < 4) --lgS;      // keep >= 4 k-steps per lane
                 const int Tp = 32 >> lgS;
@@ -270,25 +305,55 @@ __device__ __forceinline__ FactorResult factor_candidate(const FactorArgs& A, do
 #pragma unroll
                     for (int cc = 0; cc < TC; ++cc) acc[r][cc] = 0.0;
                 if (act) {
-#pragma unroll 2
-                    for (int k = s; k < 8 * J; k += S) {
-                        const int J2 = k >> 3, c = k & 7;
-                        const int H2 = npad - 8 * J2;
-                        const double* cp = Ls + blk_base(J2, npad) - 8 * J2 + c * H2 + 8 * J;   // cp[r] = L(8J+r, k)
+                    const int offc = TC * cg;
+                    int offr[TR / 2];
+#pragma unroll
+                    for (int m = 0; m < TR / 2; ++m) offr[m] = 2 * (q + Q * m);
+                    // one k-step: tile -= L(rows, k) L(panel cols, k)'   with cp[r] = L(8J + r, k)
+                    auto kstep = [&](const double* cp) {
                         double lc[TC];
 #pragma unroll
                         for (int cc = 0; cc < TC; cc += 2) {
-                            double2 v = ld2(cp + TC * cg + cc);
+                            double2 v = ld2(cp + offc + cc);
                             lc[cc] = v.x; lc[cc + 1] = v.y;
                         }
 #pragma unroll
                         for (int m = 0; m < TR / 2; ++m) {
-                            double2 lr = ld2(cp + 2 * (q + Q * m));
+                            double2 lr = ld2(cp + offr[m]);
 #pragma unroll
                             for (int cc = 0; cc < TC; ++cc) {
                                 acc[2 * m][cc] = fma(-lr.x, lc[cc], acc[2 * m][cc]);
                                 acc[2 * m + 1][cc] = fma(-lr.y, lc[cc], acc[2 * m + 1][cc]);
                             }
+                        }
+                    };
+                    if (lgS <= 3) {
+                        // lanes of one K-group take columns s, s+S, .. of EVERY earlier block column;
+                        // the 8/S k-steps per block column are unrolled for each S
+                        const double* bp = Ls + 8 * J;     // + (blk_base(J2) - 8 J2), advanced incrementally
+                        int H2 = npad;
+                        auto sweep = [&](auto lgs_tag) {
+                            constexpr int LGS = decltype(lgs_tag)::value;
+                            constexpr int NSTEP = 8 >> LGS;
+                            for (int J2 = 0; J2 < J; ++J2) {
+                                const double* cp = bp + s * H2;
+                                const int step = H2 << LGS;
+#pragma unroll
+                                for (int u = 0; u < NSTEP; ++u) { kstep(cp); cp += step; }
+                                bp += 8 * H2 - 8;
+                                H2 -= 8;
+                            }
+                        };
+                        if (lgS == 0) sweep(std::integral_constant<int, 0>{});
+                        else if (lgS == 1) sweep(std::integral_constant<int, 1>{});
+                        else if (lgS == 2) sweep(std::integral_constant<int, 2>{});
+                        else sweep(std::integral_constant<int, 3>{});
+                    } else {
+                        // S = 16 or 32: a K-group takes one column of every (S/8)-th block column
+                        const int c = s & 7;
+                        for (int J2 = s >> 3; J2 < J; J2 += (S >> 3)) {
+                            const int H2 = npad - 8 * J2;
+                            kstep(Ls + blk_base(J2, npad) - 8 * J2 + c * H2 + 8 * J);
                         }
                     }
                 }
@@ -311,7 +376,9 @@ __device__ __forceinline__ FactorResult factor_candidate(const FactorArgs& A, do
                         }
                 }
             }
+            CCGP_TW(1);
             team_sync<TEAM>();
+            CCGP_TB(1);
         }
         // ---- [B] warp 0: 8x8 diagonal block; other warps: assemble panel J+1 ---------------
         if (warp == 0) {
@@ -320,6 +387,7 @@ __device__ __forceinline__ FactorResult factor_candidate(const FactorArgs& A, do
 #pragma unroll
             for (int c = 0; c < 8; ++c) a8[c] = Ls[pbase + c * H + r];
             double dg = Ls[pbase + r * H + r];      // this row's diagonal entry, updated every step
+            double pv_own = 1.0;                     // lane 8+c keeps pivot c for the determinant
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 const double piv = __shfl_sync(0xffffffffu, dg, c);
@@ -328,8 +396,9 @@ __device__ __forceinline__ FactorResult factor_candidate(const FactorArgs& A, do
                 if (j < n) {
                     ri = rsqrt(piv);
                     if (!(piv > PIVOT_MIN)) res.bad = 1;
-                    prod_accum(res.mant_all, res.es_all, piv);
-                    if (j >= A.tail0) prod_accum(res.mant_tail, res.es_tail, piv);
+                    if (lane == c + 8) {     // lanes 8..15 idle otherwise: each tracks one column's pivot
+                        pv_own = piv;
+                    }
                 }
                 double l = a8[c] * ri;
                 if (r == c) l = piv * ri;
@@ -347,12 +416,21 @@ __device__ __forceinline__ FactorResult factor_candidate(const FactorArgs& A, do
                 for (int c = 0; c < 8; ++c)
                     if (c <= r) Ls[pbase + c * H + r] = a8[c];
             }
+            // determinant bookkeeping off the critical chain: lane 8+c folds pivot c into its own
+            // running (mantissa, exponent) pair; the 8 partial products are combined at the end
+            if (lane >= 8 && lane < 16) {
+                prod_accum(res.mant_all, res.es_all, pv_own);
+                if (8 * J + (lane - 8) >= A.tail0) prod_accum(res.mant_tail, res.es_tail, pv_own);
+            }
         }
-        if (J + 1 < NJ) {
-            if (W == 1) build_panel<DT>(A, Ls, Xs, ys, prm, J + 1, tid, TEAM);
-            else if (warp > 0) build_panel<DT>(A, Ls, Xs, ys, prm, J + 1, tid - 32, TEAM - 32);
+        if (J + 1 < NJ && (W == 1 || warp > 0)) {
+            const int gt = (W == 1) ? tid : tid - 32, gsz = (W == 1) ? TEAM : TEAM - 32;
+            if (clampx) build_panel<DT, true>(A, Ls, Xs, ys, prm, J + 1, gt, gsz);
+            else build_panel<DT, false>(A, Ls, Xs, ys, prm, J + 1, gt, gsz);
         }
+        CCGP_TW(2);
         team_sync<TEAM>();
+        CCGP_TB(2);
         // ---- [C] rows below the diagonal block, one thread per row ---------------------------
         if (H > 8) {
             double ljj[28];
@@ -382,7 +460,25 @@ __device__ __forceinline__ FactorResult factor_candidate(const FactorArgs& A, do
                 for (int c = 0; c < 8; ++c) p[c * H] = x[c];
             }
         }
+        CCGP_TW(3);
         team_sync<TEAM>();
+        CCGP_TB(3);
+    }
+    if (warp == 0) {
+        // fold the 8 per-column partial products (lanes 8..15) into lane 0, in a fixed order
+        res.bad = __any_sync(0xffffffffu, res.bad) ? 1 : 0;
+        double ma = 1.0, mt = 1.0;
+        int ea = 0, et = 0;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const double m1 = __shfl_sync(0xffffffffu, res.mant_all, 8 + c);
+            const double m2 = __shfl_sync(0xffffffffu, res.mant_tail, 8 + c);
+            const int e1 = __shfl_sync(0xffffffffu, res.es_all, 8 + c);
+            const int e2 = __shfl_sync(0xffffffffu, res.es_tail, 8 + c);
+            prod_accum(ma, ea, m1); ea += e1;
+            prod_accum(mt, et, m2); et += e2;
+        }
+        res.mant_all = ma; res.es_all = ea; res.mant_tail = mt; res.es_tail = et;
     }
     return res;
 }

@@ -166,6 +166,11 @@ int ccgp_subset_logdet_batch_dev(ccgp_ctx* ctx, const double* d_pool, int64_t N,
 int ccgp_mixed_corr(ccgp_ctx* ctx, int family, const double* params, const double* A, int na,
                     const double* B, int nb, int d, double* out);
 
+/* debug aid: clock counters per kernel phase (block 0; see tools/phase_timing.py).
+ * enable != 0 allocates/zeroes the 32-slot buffer, out32 (may be NULL) receives the
+ * current counters first; enable == 0 frees it. */
+int ccgp_debug_phase_timing(ccgp_ctx* ctx, int enable, long long* out32);
+
 #ifdef __cplusplus
 }
 #endif
