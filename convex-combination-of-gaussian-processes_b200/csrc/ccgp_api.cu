@@ -27,6 +27,7 @@ struct ccgp_ctx {
     double* d_X = nullptr;
     double* d_y = nullptr;
     double span2[MAXD] = {0};   // squared coordinate ranges of the shared design
+    std::map<std::vector<int>, uint32_t*> tiletabs;   // (n, naug, TR, TC) -> tile table
     void* ws = nullptr;       // device workspace for the host-pointer entry points
     size_t ws_bytes = 0;
     void* ws2 = nullptr;      // small device workspace (params, reductions)
@@ -74,9 +75,9 @@ typedef void (*factor_fn)(const FactorArgs);
 struct Variant { int team, tr, tc, minb; factor_fn fn_d0, fn_d2; };
 
 #define CCGP_VARIANTS(X)                                                                           \
-    X(32, 2, 4, 16) X(32, 4, 4, 16) X(64, 2, 4, 8) X(64, 4, 4, 8) X(64, 4, 8, 8) X(128, 2, 4, 4)      \
-    X(128, 4, 4, 4) X(128, 4, 8, 4) X(128, 2, 8, 4) X(256, 2, 4, 2) X(256, 4, 4, 2) X(256, 4, 8, 2)   \
-    X(128, 2, 2, 4) X(64, 2, 8, 8) X(128, 8, 4, 4) X(256, 2, 8, 2)
+    X(32, 4, 4, 16) X(32, 8, 4, 16) X(64, 4, 4, 8) X(64, 8, 4, 8) X(64, 4, 8, 8) X(128, 4, 4, 4)      \
+    X(128, 8, 4, 4) X(128, 4, 8, 4) X(256, 4, 4, 4) X(256, 8, 4, 2) X(256, 4, 8, 2) X(192, 4, 4, 4)   \
+    X(160, 4, 4, 4) X(96, 4, 4, 5) X(224, 4, 4, 4) X(192, 4, 8, 4)
 
 #define X(T, R, K, M) {T, R, K, M, factor_kernel<T, R, K, 0, M>, factor_kernel<T, R, K, 2, M>},
 static const Variant g_variants[] = {CCGP_VARIANTS(X)};
@@ -84,11 +85,43 @@ static const Variant g_variants[] = {CCGP_VARIANTS(X)};
 static const int g_num_variants = sizeof(g_variants) / sizeof(g_variants[0]);
 
 static int default_variant(const Layout& l) {
-    if (l.npad <= 24) return 0;    // 32 threads, 2x4 tiles
-    if (l.npad <= 40) return 1;    // 32 threads, 4x4 tiles
-    if (l.npad <= 72) return 3;    // 64 threads, 4x4 tiles
-    if (l.npad <= 136) return 6;   // 128 threads, 4x4 tiles
-    return 10;                     // 256 threads, 4x4 tiles
+    if (l.npad <= 40) return 0;    // 32 threads, 4x4 tiles
+    if (l.npad <= 72) return 2;    // 64 threads, 4x4 tiles
+    if (l.npad <= 136) return 5;   // 128 threads, 4x4 tiles
+    return 8;                      // 256 threads, 4x4 tiles
+}
+
+// tile table of the trailing-matrix updates: [NJ+1] first-tile index per block column, then one
+// packed entry per TR x TC tile, ordered by block column.  Within a column group (TC columns
+// of block column Jc, rows 8Jc..npad-1) tile t owns the TR/2 row pairs t, t+Nt, t+2Nt, ..
+// (Nt = tiles of the group), so consecutive tiles touch consecutive 16-byte words.
+// entry = first row | (row distance between the tile's pairs) << 10 | first column << 20
+static int get_tiletab(ccgp_ctx* ctx, const Layout& l, int TR, int TC, const uint32_t** out) {
+    std::vector<int> key = {l.n, l.naug, TR, TC};
+    auto it = ctx->tiletabs.find(key);
+    if (it != ctx->tiletabs.end()) { *out = it->second; return 0; }
+    if (l.npad >= 1024) { snprintf(ctx->err, sizeof(ctx->err), "n too large for the tile table"); return CCGP_ERR_UNSUPPORTED; }
+    std::vector<uint32_t> first((size_t)l.NJ + 1), tiles;
+    for (int Jc = 0; Jc < l.NJ; ++Jc) {
+        first[Jc] = (uint32_t)tiles.size();
+        const int H = l.npad - 8 * Jc;      // multiple of 8, so H/TR tiles of TR/2 pairs each
+        const int Nt = H / TR;
+        for (int cg = 0; cg < 8 / TC; ++cg) {
+            const int j0 = 8 * Jc + TC * cg;
+            for (int t = 0; t < Nt; ++t)
+                tiles.push_back((uint32_t)(8 * Jc + 2 * t) | ((uint32_t)(2 * Nt) << 10) | ((uint32_t)j0 << 20));
+        }
+    }
+    first[l.NJ] = (uint32_t)tiles.size();
+    std::vector<uint32_t> h(first);
+    h.insert(h.end(), tiles.begin(), tiles.end());
+    uint32_t* dptr = nullptr;
+    CK(cudaMalloc(&dptr, h.size() * 4));
+    CK(cudaMemcpyAsync(dptr, h.data(), h.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->tiletabs[key] = dptr;
+    *out = dptr;
+    return 0;
 }
 
 static int ensure_ws(ccgp_ctx* ctx, size_t bytes) {
@@ -132,6 +165,7 @@ static int launch_factor(ccgp_ctx* ctx, FactorArgs& A) {
     if (grid > A.W) grid = A.W;
     if (grid < 1) return 0;
     A.dbg = ctx->dbg;
+    RC(get_tiletab(ctx, l, var.tr, var.tc, &A.tiletab));
     fn<<<(unsigned)grid, var.team, smem, ctx->stream>>>(A);
     CK(cudaGetLastError());
     ctx->launches++;
@@ -187,6 +221,7 @@ extern "C" int ccgp_destroy(ccgp_ctx* ctx) {
     if (!ctx) return CCGP_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    for (auto& kv : ctx->tiletabs) cudaFree(kv.second);
     if (ctx->d_X) cudaFree(ctx->d_X);
     if (ctx->d_y) cudaFree(ctx->d_y);
     if (ctx->ws) cudaFree(ctx->ws);
@@ -522,6 +557,7 @@ extern "C" int ccgp_rinv_batch(ccgp_ctx* ctx, int family, int scale, const doubl
     A.cand = d_cand; A.ldc = B; A.n_params = B; A.family = family; A.logscale = scale; A.sigma2 = 1.0; A.W = B;
     A.out_mode = OUT_NLL;
     P.out_rinv = d_rinv; P.out_beta = d_beta; P.status = d_status;
+    RC(get_tiletab(ctx, l, 4, 4, &A.tiletab));
     auto fn = rinv_kernel<TEAM, 4, 4, 2>;
     CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t grid = std::min<int64_t>(B, (int64_t)ctx->num_sm * 2);
@@ -545,6 +581,7 @@ static int launch_predict(ccgp_ctx* ctx, PredictArgs& P) {
         snprintf(ctx->err, sizeof(ctx->err), "ccgp_predict: n=%d exceeds the shared-memory path", l.n);
         return CCGP_ERR_UNSUPPORTED;
     }
+    RC(get_tiletab(ctx, l, TR, TC, &P.F.tiletab));
     auto fn = predict_kernel<TEAM, TR, TC, 0, MR, TP, MINB>;
     CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int nb = 0;
@@ -579,7 +616,7 @@ extern "C" int ccgp_predict_dev(ccgp_ctx* ctx, int family, const double* d_pars,
     P.Xnew = d_Xnew; P.T = T; P.candv = d_pars_vec; P.ldcv = ldpv; P.vec_family = vec_family;
     P.out_mean = d_mean; P.out_var = d_var; P.status = d_status;
     const int n = ctx->n;
-    if (n <= 32) return launch_predict<64, 2, 4, 1, 8>(ctx, P);
+    if (n <= 32) return launch_predict<64, 4, 4, 1, 8>(ctx, P);
     if (n <= 64) return launch_predict<128, 4, 4, 2, 4>(ctx, P);
     if (n <= 128) return launch_predict<128, 4, 4, 4, 4>(ctx, P);
     if (n <= 256) return launch_predict<256, 4, 4, 8, 2>(ctx, P);

@@ -12,15 +12,16 @@
 //   z_y = L^-1 y and z_1 = L^-1 1, so the triangular solves are free.
 //   beta = z_1.z_y / z_1.z_1,  Q_R = |z_y - beta z_1|^2,  log det R = sum log piv.
 //
-// Schedule per panel J (3 team barriers):
-//   [A] every warp: K-loop  panel_J -= L[:, <8J] L[8J..8J+7, <8J]'.  Warps own disjoint
-//       row slots (no cross-warp reduction); when a warp has fewer than 32 tiles its lanes
-//       split K and the partial tiles are summed with xor-shuffles.
-//   [B] warp 0 factors the 8x8 diagonal block (lane r <-> row r, one shuffle + one rsqrt on
-//       the per-column critical chain) WHILE the other warps assemble the correlation
-//       entries of panel J+1 (2 exp per entry) -- the covariance build is the filler that
-//       hides the serial part.
-//   [C] one thread per remaining row: triangular solve against the diagonal block.
+// Schedule: the mixed correlation matrix is assembled first (all threads, 2 exp per entry);
+// then a RIGHT-LOOKING blocked Cholesky with one-panel lookahead, 3 team barriers per panel:
+//   [U1] every thread: apply factored panel J to the tiles of block column J+1;
+//   [LA] warp 0 factors the 8x8 diagonal block of panel J+1 (lane r <-> row r; one shuffle, one
+//        rsqrt, one multiply and one FMA on the per-column critical chain) WHILE the other warps
+//        apply panel J to the rest of the trailing matrix, tiles handed out from a shared counter
+//        (warp 0 joins when its serial part is done);
+//   [TS] one thread per remaining row of panel J+1: triangular solve against the diagonal block.
+// Every tile is updated by exactly one thread per step, so results do not depend on which warp
+// picked it up (bit-reproducible).
 //
 // Shared-memory layout of L ("block-column trapezoid"): block column J (8 wide)
 // stores rows 8J..npad-1 column-major with height H_J = npad-8J, block columns
@@ -111,6 +112,8 @@ struct FactorArgs {
     int64_t W;            // work items: w -> design w % n_designs, parameter row w / n_designs
     double span2[MAXD];   // squared coordinate ranges of the design (bounds the exponents)
     int force_clamp;      // 1 when span2 is unknown (per-candidate designs)
+    const uint32_t* tiletab;  // [NJ+1] first-tile index per block column, then one packed
+                              // (first row | row-pair stride << 10 | first column << 20) per tile
     long long* dbg;       // optional phase-timing buffer (tools/phase_timing.py); NULL in production
     double* out0;         // NLL: nll          DET: log det (all pivots)
     double* out1;         // NLL: beta         DET: log det (tail pivots)
@@ -228,6 +231,7 @@ __device__ __forceinline__ void build_panel(const FactorArgs& A, double* Ls, con
         for (int u = 0; u < half; ++u) {
             const int ra = lane + 32 * u, rb = ra + 32 * half;
             const int ia = 8 * J + ra, ib = 8 * J + rb;
+            const bool two = (u + half < P);                          // warp-uniform
             const int ica = min(ia, n - 1), icb = min(ib, n - 1);     // rows >= n are fixed up below
             double s1a = 0.0, s1b = 0.0;
             if (DT > 0) {
@@ -246,33 +250,156 @@ __device__ __forceinline__ void build_panel(const FactorArgs& A, double* Ls, con
                 }
             }
             double va = fma(b, dexp_neg_dev<CLAMP>(rho * s1a), a * dexp_neg_dev<CLAMP>(s1a));
-            double vb = fma(b, dexp_neg_dev<CLAMP>(rho * s1b), a * dexp_neg_dev<CLAMP>(s1b));
             if (ra <= c) va = (ra == c) ? 1.0 : 0.0;   // diagonal corner: unit diagonal, unused upper part
             if (ia >= n) va = (naug && ia == n) ? ys[j] : ((naug && ia == n + 1) ? 1.0 : 0.0);
-            if (ib >= n) vb = (naug && ib == n) ? ys[j] : ((naug && ib == n + 1) ? 1.0 : 0.0);
             if (ra < H) col[ra] = va;
-            if (rb < H && u + half < P) col[rb] = vb;
+            if (two) {
+                double vb = fma(b, dexp_neg_dev<CLAMP>(rho * s1b), a * dexp_neg_dev<CLAMP>(s1b));
+                if (ib >= n) vb = (naug && ib == n) ? ys[j] : ((naug && ib == n + 1) ? 1.0 : 0.0);
+                if (rb < H) col[rb] = vb;
+            }
         }
     }
 }
 
-// Build A panel by panel and factor it in place.  All threads of the team call this.
+// 1/sqrt(x) for a normal positive x: MUFU.RSQ64H seed (2^-22) + one cubic correction, no
+// special-case path (pivots are screened against PIVOT_MIN separately)
+__device__ __forceinline__ double fast_rsqrt(double x) {
+    double y0;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
+    const double t = y0 * y0;
+    const double e = fma(x, -t, 1.0);
+    const double p = fma(e, 0.375, 0.5);
+    const double ye = y0 * e;
+    return fma(p, ye, y0);
+}
+
+// trailing update of one TR x TC tile with the 8 columns of factored panel J:
+//   C -= L(rows, 8J..8J+7) L(j0.., 8J..8J+7)'
+// The tile's TR rows are TR/2 row PAIRS (ia + m*rs, +1): consecutive tiles of a column group
+// take consecutive pairs, so the double2 loads/stores of consecutive lanes are consecutive
+// 16-byte words (bank-conflict free); the TC panel-row values are broadcasts.
+template <int TR, int TC>
+__device__ __forceinline__ void tile_update(double* Ls, int npad, int J, int ia, int rs, int j0) {
+    const int HJ = npad - 8 * J;
+    const double* pJ = Ls + blk_base(J, npad) - 8 * J;             // L(i, 8J+k) at pJ + k*HJ + i
+    const int Jc = j0 >> 3, HC = npad - 8 * Jc;
+    double* cb = Ls + blk_base(Jc, npad) + (j0 - 8 * Jc) * HC + (ia - 8 * Jc);   // C(ia, j0); next column + HC
+    double acc[TR][TC];
+#pragma unroll
+    for (int cc = 0; cc < TC; ++cc)
+#pragma unroll
+        for (int m = 0; m < TR / 2; ++m) {
+            double2 v = ld2(cb + cc * HC + m * rs);
+            acc[2 * m][cc] = v.x; acc[2 * m + 1][cc] = v.y;
+        }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const double* cp = pJ + k * HJ;
+        double lr[TR], lc[TC];
+#pragma unroll
+        for (int m = 0; m < TR / 2; ++m) { double2 v = ld2(cp + ia + m * rs); lr[2 * m] = v.x; lr[2 * m + 1] = v.y; }
+#pragma unroll
+        for (int m = 0; m < TC / 2; ++m) { double2 v = ld2(cp + j0 + 2 * m); lc[2 * m] = v.x; lc[2 * m + 1] = v.y; }
+#pragma unroll
+        for (int r = 0; r < TR; ++r)
+#pragma unroll
+            for (int cc = 0; cc < TC; ++cc) acc[r][cc] = fma(-lr[r], lc[cc], acc[r][cc]);
+    }
+#pragma unroll
+    for (int cc = 0; cc < TC; ++cc)
+#pragma unroll
+        for (int m = 0; m < TR / 2; ++m)
+            *reinterpret_cast<double2*>(cb + cc * HC + m * rs) = make_double2(acc[2 * m][cc], acc[2 * m + 1][cc]);
+}
+
+// ---- 8x8 diagonal block of panel J: warp-level, lane r <-> row r (lanes >= 8 mirror) ---------
+// Per column the critical chain is one shuffle (the pivot), one rsqrt, one multiply and one FMA
+// (each row keeps its own diagonal entry `dg` current so the next pivot needs no second shuffle).
+__device__ __forceinline__ void diag_block(const FactorArgs& A, double* Ls, double* rinv_s, int J, int lane,
+                                           FactorResult& res) {
+    const int n = A.lay.n, npad = A.lay.npad;
+    const int H = npad - 8 * J, pbase = blk_base(J, npad);
+    const int r = lane & 7;
+    double a8[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) a8[c] = Ls[pbase + c * H + r];
+    double dg = Ls[pbase + r * H + r];
+    double pv_own = 1.0;                     // lane 8+c keeps pivot c for the determinant
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const double piv = __shfl_sync(0xffffffffu, dg, c);
+        const bool live = (8 * J + c) < n;
+        const double ri = live ? fast_rsqrt(piv) : 0.0;
+        if (live && !(piv > PIVOT_MIN)) res.bad = 1;
+        if (live && lane == c + 8) pv_own = piv;
+        double l = a8[c] * ri;
+        if (r > c) dg = fma(-l, l, dg);
+        if (r == c) l = piv * ri;
+        a8[c] = l;
+        double lc2[8];
+#pragma unroll
+        for (int c2 = c + 1; c2 < 8; ++c2) lc2[c2] = __shfl_sync(0xffffffffu, l, c2);
+#pragma unroll
+        for (int c2 = c + 1; c2 < 8; ++c2) a8[c2] = fma(-l, lc2[c2], a8[c2]);
+        if (lane == 0) rinv_s[c] = ri;
+    }
+    if (lane < 8) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+            if (c <= r) Ls[pbase + c * H + r] = a8[c];
+    }
+    // determinant bookkeeping off the critical chain: lane 8+c folds pivot c into its own running
+    // (mantissa, exponent) pair; the 8 partial products are combined once per candidate
+    if (lane >= 8 && lane < 16) {
+        prod_accum(res.mant_all, res.es_all, pv_own);
+        if (8 * J + (lane - 8) >= A.tail0) prod_accum(res.mant_tail, res.es_tail, pv_own);
+    }
+}
+
+// ---- rows below the diagonal block of panel J: one thread per row, x L_JJ' = a -----------------
+template <int TEAM>
+__device__ __forceinline__ void panel_trsm(double* Ls, const double* rinv_s, int npad, int J, int tid) {
+    const int H = npad - 8 * J, pbase = blk_base(J, npad);
+    const double* dj = Ls + pbase;            // L_JJ(c, c1) at dj[c1*H + c] (warp-wide broadcast loads)
+    for (int t = tid; t < H - 8; t += TEAM) {
+        double* p = Ls + pbase + 8 + t;
+        double x[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) x[c] = p[c * H];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+#pragma unroll
+            for (int c1 = 0; c1 < c; ++c1) x[c] = fma(-x[c1], dj[c1 * H + c], x[c]);
+            x[c] *= rinv_s[c];
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) p[c * H] = x[c];
+    }
+}
+
+// Build A, then right-looking blocked Cholesky with one-panel lookahead.  All threads of the team
+// call this.  `ctr` is one shared int (dynamic tile counter).
 template <int TEAM, int TR, int TC, int DT>
 __device__ __forceinline__ FactorResult factor_candidate(const FactorArgs& A, double* Ls, const double* Xs,
-                                                         const double* ys, double* rinv_s, const Prm* prm) {
-    static_assert(TR == 2 || TR == 4 || TR == 8, "TR");
-    static_assert(TC == 2 || TC == 4 || TC == 8, "TC");
+                                                         const double* ys, double* rinv_s, const Prm* prm, int* ctr) {
+    static_assert(TR == 4 || TR == 8, "TR");
+    static_assert(TC == 4 || TC == 8, "TC");
     constexpr int W = TEAM / 32;
-    constexpr int CG = 8 / TC;
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    const int n = A.lay.n, npad = A.lay.npad, NJ = A.lay.NJ;
+    const int npad = A.lay.npad, NJ = A.lay.NJ;
+    const uint32_t* first = A.tiletab;               // first[Jc]: index of the first tile of block column Jc
+    const uint32_t* tiles = A.tiletab + NJ + 1;
+    const int ntiles = (int)__ldg(first + NJ);
 
-    const bool clampx = prm->clamp != 0;
     CCGP_T0();
-    if (clampx) build_panel<DT, true>(A, Ls, Xs, ys, prm, 0, tid, TEAM);
-    else build_panel<DT, false>(A, Ls, Xs, ys, prm, 0, tid, TEAM);
+    const bool clampx = prm->clamp != 0;
+    for (int J = 0; J < NJ; ++J) {
+        if (clampx) build_panel<DT, true>(A, Ls, Xs, ys, prm, J, tid, TEAM);
+        else build_panel<DT, false>(A, Ls, Xs, ys, prm, J, tid, TEAM);
+    }
     CCGP_TW(0);
     team_sync<TEAM>();
     CCGP_TB(0);
@@ -280,186 +407,43 @@ __device__ __forceinline__ FactorResult factor_candidate(const FactorArgs& A, do
     FactorResult res;
     res.mant_all = 1.0; res.mant_tail = 1.0; res.es_all = 0; res.es_tail = 0; res.bad = 0;
 
-    for (int J = 0; J < NJ; ++J) {
-        const int H = npad - 8 * J;
-        const int pbase = blk_base(J, npad);
-        // ---- [A] left-looking update of panel J with block columns < J ---------------------
-        if (J > 0) {
-            const int Q = H / TR;                 // row slots
-            const int T = Q * CG;                 // tiles of the panel
-            const int Tw = (T + W - 1) / W;       // tiles per warp (blocked)
-            for (int t0 = 0; t0 < Tw; t0 += 32) {
-                const int Tc = min(Tw - t0, 32);
-                const int lg = (Tc <= 1) ? 0 : 32 - __clz(Tc - 1);      // ceil(log2(Tc))
-                int lgS = 5 - lg;                                   // in-warp K-split = 2^lgS
-                while (lgS > 0 && ((8 * J) >> lgS) < 4) --lgS;      // keep >= 4 k-steps per lane
-                const int Tp = 32 >> lgS;
-                const int S = 1 << lgS;
-                const int tl = lane & (Tp - 1), s = lane / Tp;
-                const int t = warp * Tw + t0 + tl;
-                const bool act = (tl < Tc) && (t < T);
-                const int q = act ? t / CG : 0, cg = act ? t % CG : 0;
-                double acc[TR][TC];
-#pragma unroll
-                for (int r = 0; r < TR; ++r)
-#pragma unroll
-                    for (int cc = 0; cc < TC; ++cc) acc[r][cc] = 0.0;
-                if (act) {
-                    const int offc = TC * cg;
-                    int offr[TR / 2];
-#pragma unroll
-                    for (int m = 0; m < TR / 2; ++m) offr[m] = 2 * (q + Q * m);
-                    // one k-step: tile -= L(rows, k) L(panel cols, k)'   with cp[r] = L(8J + r, k)
-                    auto kstep = [&](const double* cp) {
-                        double lc[TC];
-#pragma unroll
-                        for (int cc = 0; cc < TC; cc += 2) {
-                            double2 v = ld2(cp + offc + cc);
-                            lc[cc] = v.x; lc[cc + 1] = v.y;
-                        }
-#pragma unroll
-                        for (int m = 0; m < TR / 2; ++m) {
-                            double2 lr = ld2(cp + offr[m]);
-#pragma unroll
-                            for (int cc = 0; cc < TC; ++cc) {
-                                acc[2 * m][cc] = fma(-lr.x, lc[cc], acc[2 * m][cc]);
-                                acc[2 * m + 1][cc] = fma(-lr.y, lc[cc], acc[2 * m + 1][cc]);
-                            }
-                        }
-                    };
-                    if (lgS <= 3) {
-                        // lanes of one K-group take columns s, s+S, .. of EVERY earlier block column;
-                        // the 8/S k-steps per block column are unrolled for each S
-                        const double* bp = Ls + 8 * J;     // + (blk_base(J2) - 8 J2), advanced incrementally
-                        int H2 = npad;
-                        auto sweep = [&](auto lgs_tag) {
-                            constexpr int LGS = decltype(lgs_tag)::value;
-                            constexpr int NSTEP = 8 >> LGS;
-                            for (int J2 = 0; J2 < J; ++J2) {
-                                const double* cp = bp + s * H2;
-                                const int step = H2 << LGS;
-#pragma unroll
-                                for (int u = 0; u < NSTEP; ++u) { kstep(cp); cp += step; }
-                                bp += 8 * H2 - 8;
-                                H2 -= 8;
-                            }
-                        };
-                        if (lgS == 0) sweep(std::integral_constant<int, 0>{});
-                        else if (lgS == 1) sweep(std::integral_constant<int, 1>{});
-                        else if (lgS == 2) sweep(std::integral_constant<int, 2>{});
-                        else sweep(std::integral_constant<int, 3>{});
-                    } else {
-                        // S = 16 or 32: a K-group takes one column of every (S/8)-th block column
-                        const int c = s & 7;
-                        for (int J2 = s >> 3; J2 < J; J2 += (S >> 3)) {
-                            const int H2 = npad - 8 * J2;
-                            kstep(Ls + blk_base(J2, npad) - 8 * J2 + c * H2 + 8 * J);
-                        }
-                    }
-                }
-                for (int o = Tp; o < 32; o <<= 1) {
-#pragma unroll
-                    for (int r = 0; r < TR; ++r)
-#pragma unroll
-                        for (int cc = 0; cc < TC; ++cc) acc[r][cc] += __shfl_xor_sync(0xffffffffu, acc[r][cc], o);
-                }
-                if (act && s == 0) {
-#pragma unroll
-                    for (int m = 0; m < TR / 2; ++m)
-#pragma unroll
-                        for (int cc = 0; cc < TC; ++cc) {
-                            double2* dst = reinterpret_cast<double2*>(Ls + pbase + (TC * cg + cc) * H + 2 * (q + Q * m));
-                            double2 v = *dst;
-                            v.x += acc[2 * m][cc];
-                            v.y += acc[2 * m + 1][cc];
-                            *dst = v;
-                        }
-                }
-            }
-            CCGP_TW(1);
-            team_sync<TEAM>();
-            CCGP_TB(1);
+    if (warp == 0) diag_block(A, Ls, rinv_s, 0, lane, res);
+    team_sync<TEAM>();
+    panel_trsm<TEAM>(Ls, rinv_s, npad, 0, tid);
+    CCGP_TW(3);
+    team_sync<TEAM>();
+    CCGP_TB(3);
+
+    for (int J = 0; J + 1 < NJ; ++J) {
+        // ---- U1: bring block column J+1 up to date with panel J (every thread) --------------
+        const int t1 = (int)__ldg(first + J + 1), t2 = (int)__ldg(first + J + 2);
+        for (int t = t1 + tid; t < t2; t += TEAM) {
+            const uint32_t e = __ldg(tiles + t);
+            tile_update<TR, TC>(Ls, npad, J, e & 0x3ff, (e >> 10) & 0x3ff, e >> 20);
         }
-        // ---- [B] warp 0: 8x8 diagonal block; other warps: assemble panel J+1 ---------------
-        if (warp == 0) {
-            const int r = lane & 7;
-            double a8[8];
-#pragma unroll
-            for (int c = 0; c < 8; ++c) a8[c] = Ls[pbase + c * H + r];
-            double dg = Ls[pbase + r * H + r];      // this row's diagonal entry, updated every step
-            double pv_own = 1.0;                     // lane 8+c keeps pivot c for the determinant
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const double piv = __shfl_sync(0xffffffffu, dg, c);
-                const int j = 8 * J + c;
-                double ri = 0.0;
-                if (j < n) {
-                    ri = rsqrt(piv);
-                    if (!(piv > PIVOT_MIN)) res.bad = 1;
-                    if (lane == c + 8) {     // lanes 8..15 idle otherwise: each tracks one column's pivot
-                        pv_own = piv;
-                    }
-                }
-                double l = a8[c] * ri;
-                if (r == c) l = piv * ri;
-                a8[c] = l;
-                if (r > c) dg = fma(-l, l, dg);
-#pragma unroll
-                for (int c2 = c + 1; c2 < 8; ++c2) {
-                    const double lc2 = __shfl_sync(0xffffffffu, l, c2);
-                    a8[c2] = fma(-l, lc2, a8[c2]);
-                }
-                if (lane == 0) rinv_s[c] = ri;
+        if (tid == 0) *ctr = t2;
+        CCGP_TW(1);
+        team_sync<TEAM>();
+        CCGP_TB(1);
+        // ---- lookahead: warp 0 factors the diagonal block of panel J+1 while the others apply
+        //      panel J to the rest of the trailing matrix; warp 0 joins when it is done ---------
+        if (warp == 0) diag_block(A, Ls, rinv_s, J + 1, lane, res);
+        for (;;) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(ctr, 32);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base >= ntiles) break;
+            const int t = base + lane;
+            if (t < ntiles) {
+                const uint32_t e = __ldg(tiles + t);
+                tile_update<TR, TC>(Ls, npad, J, e & 0x3ff, (e >> 10) & 0x3ff, e >> 20);
             }
-            if (lane < 8) {
-#pragma unroll
-                for (int c = 0; c < 8; ++c)
-                    if (c <= r) Ls[pbase + c * H + r] = a8[c];
-            }
-            // determinant bookkeeping off the critical chain: lane 8+c folds pivot c into its own
-            // running (mantissa, exponent) pair; the 8 partial products are combined at the end
-            if (lane >= 8 && lane < 16) {
-                prod_accum(res.mant_all, res.es_all, pv_own);
-                if (8 * J + (lane - 8) >= A.tail0) prod_accum(res.mant_tail, res.es_tail, pv_own);
-            }
-        }
-        if (J + 1 < NJ && (W == 1 || warp > 0)) {
-            const int gt = (W == 1) ? tid : tid - 32, gsz = (W == 1) ? TEAM : TEAM - 32;
-            if (clampx) build_panel<DT, true>(A, Ls, Xs, ys, prm, J + 1, gt, gsz);
-            else build_panel<DT, false>(A, Ls, Xs, ys, prm, J + 1, gt, gsz);
         }
         CCGP_TW(2);
         team_sync<TEAM>();
         CCGP_TB(2);
-        // ---- [C] rows below the diagonal block, one thread per row ---------------------------
-        if (H > 8) {
-            double ljj[28];
-            double ri[8];
-            {
-                int t = 0;
-#pragma unroll
-                for (int c = 1; c < 8; ++c)
-#pragma unroll
-                    for (int c1 = 0; c1 < c; ++c1) ljj[t++] = Ls[pbase + c1 * H + c];
-#pragma unroll
-                for (int c = 0; c < 8; ++c) ri[c] = rinv_s[c];
-            }
-            for (int t = tid; t < H - 8; t += TEAM) {
-                double* p = Ls + pbase + 8 + t;
-                double x[8];
-#pragma unroll
-                for (int c = 0; c < 8; ++c) x[c] = p[c * H];
-                int u = 0;
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-#pragma unroll
-                    for (int c1 = 0; c1 < c; ++c1) x[c] = fma(-x[c1], ljj[u++], x[c]);
-                    x[c] *= ri[c];
-                }
-#pragma unroll
-                for (int c = 0; c < 8; ++c) p[c * H] = x[c];
-            }
-        }
+        // ---- rows of panel J+1 below its diagonal block ---------------------------------------
+        panel_trsm<TEAM>(Ls, rinv_s, npad, J + 1, tid);
         CCGP_TW(3);
         team_sync<TEAM>();
         CCGP_TB(3);
@@ -536,6 +520,7 @@ __global__ void __launch_bounds__(TEAM, MINB) factor_kernel(const FactorArgs A) 
     double* rinv_s = ys + lay.npx;
     double* red = rinv_s + 8;
     Prm* prm = reinterpret_cast<Prm*>(red + 64);
+    int* ctr = reinterpret_cast<int*>(reinterpret_cast<char*>(prm) + sizeof(Prm));
     const int tid = threadIdx.x;
     const int n = lay.n, npad = lay.npad;
 
@@ -555,7 +540,7 @@ __global__ void __launch_bounds__(TEAM, MINB) factor_kernel(const FactorArgs A) 
         if (A.design_mode != DESIGN_SHARED) stage_design<TEAM>(A, dsg, Xs);
         team_sync<TEAM>();
 
-        FactorResult res = factor_candidate<TEAM, TR, TC, DT>(A, Ls, Xs, ys, rinv_s, prm);
+        FactorResult res = factor_candidate<TEAM, TR, TC, DT>(A, Ls, Xs, ys, rinv_s, prm, ctr);
 
         if (A.out_mode == OUT_NLL) {
             double s11 = 0.0, s1y = 0.0;
