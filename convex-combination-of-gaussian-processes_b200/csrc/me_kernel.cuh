@@ -1,8 +1,214 @@
-// me_kernel.cuh -- (stub until the specialised ME kernel lands; generic engine is used)
+// me_kernel.cuh -- specialised kernel for the maximum-entropy batch criterion
+// `Augmented.Mixed.Entropy` ([M]:869-877): -det(R.new - R.cross R.old^-1 R.cross') for C
+// candidate second-batch designs x P parameter rows, small sizes (n_new <= 8, n_old <= 32,
+// d <= 4; the reference runs n_old = 14, n_new = 7, d = 2).
+//
+// The Schur complement is the trailing block of the Cholesky factor of
+//   R_all = [ R.old  R.cross' ; R.cross  R.new ],
+// so with R.old = L_o L_o' (factored ONCE per parameter row, [M]:924-925 computes R.old.Inv
+// once per row too) each candidate needs  A = R.cross L_o^-T  (n_new forward solves),
+// S = R.new - A A'  and the product of the n_new Cholesky pivots of S.
+//
+// Mapping: a CTA takes (parameter row, chunk of candidates); it factors R.old into shared
+// memory, then every 8-lane group owns one candidate, lane r <-> new point r: the cross
+// correlations and the forward solve of row r stay in that lane's registers, rows are
+// exchanged through a per-warp shared buffer for S, and the 8x8 factorisation runs on
+// width-8 shuffles.  Deterministic: one fixed evaluation order per (candidate, row).
 #pragma once
 #include "factor_engine.cuh"
+
 namespace ccgp {
-inline bool me_fast_supported(int, int, int) { return false; }
-inline int me_fast_launch(cudaStream_t, int, const double*, int, int, const double*, int, int64_t, const double*, int64_t,
-                          int64_t, double*, double*, int32_t*, char*, size_t) { return -3; }
+
+struct MeArgs {
+    const double* D_old;   // n_old x d column-major
+    const double* D_new;   // C blocks of n_new*d (each n_new x d column-major)
+    const double* params;  // P x 3 column-major (p, theta1, theta2), ld ldq
+    int64_t ldq;
+    int n_old, n_new, d;
+    int64_t C, P;
+    int64_t chunk;         // candidates per work item
+    int64_t nchunks;       // ceil(C / chunk)
+    double* negdet;        // C x P column-major (may be NULL)
+    double* logdet;        // (may be NULL)
+    int32_t* status;       // (may be NULL)
+};
+
+inline bool me_fast_supported(int n_old, int n_new, int d) {
+    return n_new >= 1 && n_new <= 8 && n_old >= 1 && n_old <= 32 && d >= 1 && d <= 4;
 }
+
+template <int NOLD>
+__global__ void __launch_bounds__(128) me_schur_kernel(const MeArgs M) {
+    constexpr int DM = 4;
+    __shared__ double Lo[NOLD * NOLD];        // L_old, row-major Lo[j*NOLD + k], k <= j
+    __shared__ double rio[NOLD];              // 1 / L_old(j,j)
+    __shared__ double Xo[DM * NOLD];          // D_old, Xo[k*NOLD + j]
+    __shared__ double abuf[4][32][NOLD + 1];  // per warp: the solved cross rows (padded against conflicts)
+    __shared__ double prm[4];                 // a, b, theta1, theta2
+    __shared__ int s_bad;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_old = M.n_old, n_new = M.n_new, d = M.d;
+    const int r = lane & 7, grp = lane >> 3;
+    const unsigned full = 0xffffffffu;
+
+    for (int e = tid; e < DM * NOLD; e += 128) {
+        int k = e / NOLD, j = e - k * NOLD;
+        Xo[e] = (k < d && j < n_old) ? M.D_old[k * n_old + j] : 0.0;
+    }
+
+    const int64_t nitems = M.P * M.nchunks;
+    for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const int64_t q = item / M.nchunks, ch = item - q * M.nchunks;
+        __syncthreads();
+        if (tid == 0) {
+            const double p = M.params[q], t1 = M.params[q + M.ldq], t2 = M.params[q + 2 * M.ldq];
+            const double w = p * p + (1.0 - p) * (1.0 - p);
+            prm[0] = p * p / w; prm[1] = (1.0 - p) * (1.0 - p) / w; prm[2] = t1; prm[3] = t2;
+            s_bad = 0;
+        }
+        __syncthreads();
+        const double ca = prm[0], cb = prm[1], t1 = prm[2], t2 = prm[3];
+        // ---- R.old (lower) into Lo, identity padding beyond n_old ---------------------------
+        for (int e = tid; e < NOLD * NOLD; e += 128) {
+            int j = e / NOLD, k = e - j * NOLD;
+            double v = (j == k) ? 1.0 : 0.0;
+            if (k < j && j < n_old) {
+                double s = 0.0;
+#pragma unroll
+                for (int dd = 0; dd < DM; ++dd) { double df = Xo[dd * NOLD + j] - Xo[dd * NOLD + k]; s = fma(df, df, s); }
+                v = fma(cb, dexp_neg_dev<true>(t2 * s), ca * dexp_neg_dev<true>(t1 * s));
+            }
+            Lo[e] = v;
+        }
+        __syncthreads();
+        // ---- Cholesky of R.old by warp 0: lane <-> row, right-looking, column by column --------
+        if (warp == 0) {
+            int bad = 0;
+            for (int j = 0; j < n_old; ++j) {
+                const double piv = Lo[j * NOLD + j];
+                if (!(piv > PIVOT_MIN)) bad = 1;
+                const double ri = fast_rsqrt(piv);
+                __syncwarp();
+                double lij = 0.0;
+                if (lane < NOLD && lane > j) { lij = Lo[lane * NOLD + j] * ri; Lo[lane * NOLD + j] = lij; }
+                if (lane == j) { Lo[j * NOLD + j] = piv * ri; rio[j] = ri; }
+                __syncwarp();
+                if (lane < NOLD && lane > j)
+                    for (int k = j + 1; k <= lane; ++k) Lo[lane * NOLD + k] = fma(-lij, Lo[k * NOLD + j], Lo[lane * NOLD + k]);
+                __syncwarp();
+            }
+            if (lane >= n_old && lane < NOLD) rio[lane] = 1.0;
+            if (bad && lane == 0) s_bad = 1;
+        }
+        __syncthreads();
+        const int bad_old = s_bad;
+
+        // ---- candidates of this chunk: 16 per pass (4 warps x 4 groups) -----------------------
+        const int64_t c_lo = ch * M.chunk, c_hi = min(M.C, c_lo + M.chunk);
+        for (int64_t c0 = c_lo; c0 < c_hi; c0 += 16) {
+            const int64_t c = c0 + warp * 4 + grp;
+            const bool valid = c < c_hi;
+            const bool rowok = valid && r < n_new;
+            double x[DM];
+#pragma unroll
+            for (int dd = 0; dd < DM; ++dd)
+                x[dd] = (rowok && dd < d) ? M.D_new[c * (int64_t)(n_new * d) + dd * n_new + r] : 0.0;
+            // cross correlations of new point r with the old design, then a = L_o^-1 (.)
+            double a[NOLD];
+#pragma unroll
+            for (int j = 0; j < NOLD; ++j) {
+                double s = 0.0;
+#pragma unroll
+                for (int dd = 0; dd < DM; ++dd) { double df = x[dd] - Xo[dd * NOLD + j]; s = fma(df, df, s); }
+                a[j] = (j < n_old) ? fma(cb, dexp_neg_dev<true>(t2 * s), ca * dexp_neg_dev<true>(t1 * s)) : 0.0;
+            }
+#pragma unroll
+            for (int j = 0; j < NOLD; ++j) {
+#pragma unroll
+                for (int k = 0; k < j; ++k) a[j] = fma(-a[k], Lo[j * NOLD + k], a[j]);
+                a[j] *= rio[j];
+            }
+            double* mine = &abuf[warp][lane][0];
+#pragma unroll
+            for (int j = 0; j < NOLD; ++j) mine[j] = a[j];
+            __syncwarp();
+            // row r of S = R.new - A A' (entries c2 <= r), new-new correlations by shuffled coordinates
+            double s8[8];
+#pragma unroll
+            for (int c2 = 0; c2 < 8; ++c2) {
+                double sq = 0.0;
+#pragma unroll
+                for (int dd = 0; dd < DM; ++dd) {
+                    const double xc = __shfl_sync(full, x[dd], c2, 8);
+                    const double df = x[dd] - xc;
+                    sq = fma(df, df, sq);
+                }
+                double v = fma(cb, dexp_neg_dev<true>(t2 * sq), ca * dexp_neg_dev<true>(t1 * sq));
+                if (c2 == r) v = 1.0;
+                const double* other = &abuf[warp][(lane & ~7) + c2][0];
+                double dot = 0.0;
+#pragma unroll
+                for (int j = 0; j < NOLD; ++j) dot = fma(a[j], other[j], dot);
+                v -= dot;
+                // rows/columns beyond n_new: identity padding
+                if (r >= n_new || c2 >= n_new) v = (c2 == r) ? 1.0 : 0.0;
+                s8[c2] = v;
+            }
+            __syncwarp();
+            // 8x8 Cholesky inside the 8-lane group; only the pivots are needed
+            double dg = 1.0;
+#pragma unroll
+            for (int c2 = 0; c2 < 8; ++c2) if (c2 == r) dg = s8[c2];
+            double mant = 1.0;
+            int es = 0, bad = bad_old;
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc) {
+                const double piv = __shfl_sync(full, dg, cc, 8);
+                if (cc < n_new) {
+                    if (!(piv > PIVOT_MIN)) bad = 1;
+                    prod_accum(mant, es, piv);
+                }
+                const double ri = fast_rsqrt(piv);
+                double l = s8[cc] * ri;
+                if (r > cc) dg = fma(-l, l, dg);
+                double lc2[8];
+#pragma unroll
+                for (int c2 = cc + 1; c2 < 8; ++c2) lc2[c2] = __shfl_sync(full, l, c2, 8);
+#pragma unroll
+                for (int c2 = cc + 1; c2 < 8; ++c2) s8[c2] = fma(-l, lc2[c2], s8[c2]);
+            }
+            if (valid && r == 0) {
+                const int64_t o = c + M.C * q;
+                const double nanv = __longlong_as_double(0x7ff8000000000000LL);
+                if (M.negdet) M.negdet[o] = bad ? nanv : -scalbn(mant, es);
+                if (M.logdet) M.logdet[o] = bad ? nanv : log(mant) + es * LN2;
+                if (M.status) M.status[o] = bad ? 1 : 0;
+            }
+            __syncwarp();
+        }
+    }
+}
+
+inline int me_fast_launch(cudaStream_t stream, int num_sm, const double* d_D_old, int n_old, int d,
+                          const double* d_D_new, int n_new, int64_t C, const double* d_params, int64_t P,
+                          int64_t ldq, double* d_negdet, double* d_logdet, int32_t* d_status, char* err, size_t errlen) {
+    MeArgs M;
+    M.D_old = d_D_old; M.D_new = d_D_new; M.params = d_params; M.ldq = ldq;
+    M.n_old = n_old; M.n_new = n_new; M.d = d; M.C = C; M.P = P;
+    // enough candidates per work item to amortise the R.old factorisation, enough items to fill the GPU
+    int64_t chunk = 256;
+    const int64_t target_items = (int64_t)num_sm * 8;
+    while (chunk > 16 && P * ((C + chunk - 1) / chunk) < target_items) chunk >>= 1;
+    M.chunk = chunk;
+    M.nchunks = (C + chunk - 1) / chunk;
+    M.negdet = d_negdet; M.logdet = d_logdet; M.status = d_status;
+    const int64_t items = P * M.nchunks;
+    const int grid = (int)std::min<int64_t>(items, (int64_t)num_sm * 8);
+    if (n_old <= 16) me_schur_kernel<16><<<grid, 128, 0, stream>>>(M);
+    else me_schur_kernel<32><<<grid, 128, 0, stream>>>(M);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { snprintf(err, errlen, "me_schur_kernel launch: %s", cudaGetErrorString(e)); return -2; }
+    return 0;
+}
+
+}  // namespace ccgp
