@@ -1,12 +1,308 @@
-// bigchol.cuh -- (stub until the blocked large-n path lands)
+// bigchol.cuh -- blocked path for designs too large for shared memory (n up to a few
+// thousand; SURVEY 8d ME-B: the synthetic n = 2048, 2-D anisotropic scaling case).
+//
+// Same likelihood as factor_engine.cuh (logpost [A]:444-455 / cond.like [V]:564-575), same
+// augmented-matrix trick, but every candidate's matrix lives in HBM (column-major, leading
+// dimension nrp) and the factorisation is a right-looking blocked Cholesky, block size 64,
+// one launch per stage and step, batched over the candidates of a chunk:
+//   build    : mixed correlation tiles (2 exp per entry) + identity padding + rows y', 1'
+//   potrf64  : 64x64 diagonal block in shared memory (one CTA per candidate)
+//   trsm64   : rows below, one thread per row against the diagonal block in shared memory
+//   syrk64   : trailing update C_ij -= P_i P_j' on the FP64 tensor path
+//              (mma.sync.m8n8k4.f64 -> DMMA; tcgen05 has no FP64 kind) -- the only place in
+//              this library where the update is a dense contraction big enough to feed it
+//   finish   : z-dots, beta, Q_R, log det -> NLL
+// Row layout: [0,n) design points, [n,ncp) identity padding (ncp = n rounded up to 64),
+// rows ncp and ncp+1 are y' and 1', zero rows up to nrp = ncp + 64.
 #pragma once
+#include <algorithm>
 #include "factor_engine.cuh"
+
 namespace ccgp {
-struct BigCholWorkspace { void release() {} };
-inline int bigchol_nll_batch(BigCholWorkspace&, cudaStream_t, int, const double*, const double*, int n, int, int, int,
-                             const double*, int64_t, int64_t, double, int, double, double*, double*, int32_t*, int64_t*,
-                             char* err, size_t errlen) {
-    snprintf(err, errlen, "n=%d exceeds the shared-memory path and the blocked path is not built", n);
-    return -3;
+
+struct BigCholWorkspace {
+    double* A = nullptr;       // chunk * nrp * ncp
+    double* logdet = nullptr;  // chunk
+    int* bad = nullptr;        // chunk
+    Prm* prm = nullptr;        // chunk
+    size_t bytesA = 0;
+    int cap = 0;
+    void release() {
+        if (A) cudaFree(A);
+        if (logdet) cudaFree(logdet);
+        if (bad) cudaFree(bad);
+        if (prm) cudaFree(prm);
+        A = nullptr; logdet = nullptr; bad = nullptr; prm = nullptr; bytesA = 0; cap = 0;
+    }
+};
+
+struct BigArgs {
+    double* A;
+    int n, d, ncp, nrp;
+    int64_t stride;            // nrp * ncp
+    const double* X;           // n x d column-major
+    const double* y;
+    const Prm* prm;
+    double* logdet;
+    int* bad;
+};
+
+__global__ void __launch_bounds__(128) big_params_kernel(FactorArgs F, int64_t b0, int nb, Prm* prm, double* logdet, int* bad) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < nb) {
+        load_params(F, b0 + b, prm + b);
+        logdet[b] = 0.0;
+        bad[b] = 0;
+    }
 }
+
+// one CTA (256 threads) per (64x64 tile on or below the diagonal incl. the extra rows, candidate)
+__global__ void __launch_bounds__(256) big_build_kernel(BigArgs G) {
+    const int b = blockIdx.z, ti = blockIdx.y, tj = blockIdx.x;
+    if (ti < tj) return;
+    const Prm* pr = G.prm + b;
+    __shared__ double xi[MAXD][64], xj[MAXD][64], wts[MAXD];
+    const int tid = threadIdx.x, n = G.n, d = G.d;
+    for (int e = tid; e < d * 64; e += 256) {
+        int k = e / 64, r = e % 64;
+        int i = ti * 64 + r, j = tj * 64 + r;
+        xi[k][r] = (i < n) ? G.X[(size_t)k * n + i] : 0.0;
+        xj[k][r] = (j < n) ? G.X[(size_t)k * n + j] : 0.0;
+    }
+    if (tid < d) wts[tid] = pr->wts[tid];
+    __syncthreads();
+    const double rho = pr->rho, a = pr->a, bb = pr->b;
+    double* Ab = G.A + (size_t)b * G.stride;
+    for (int e = tid; e < 64 * 64; e += 256) {
+        const int r = e % 64, c = e / 64;
+        const int i = ti * 64 + r, j = tj * 64 + c;
+        double v = 0.0;
+        if (i < n && j < n) {
+            if (i == j) v = 1.0;
+            else if (i > j) {
+                double s1 = 0.0;
+                for (int k = 0; k < d; ++k) { double df = xi[k][r] - xj[k][c]; s1 = fma(wts[k] * df, df, s1); }
+                v = fma(bb, dexp_neg_dev<true>(rho * s1), a * dexp_neg_dev<true>(s1));
+            }
+        } else if (i == j) v = 1.0;                       // identity padding (i, j in [n, ncp))
+        else if (j < n && i == G.ncp) v = G.y[j];         // row y'
+        else if (j < n && i == G.ncp + 1) v = 1.0;        // row 1'
+        Ab[(size_t)j * G.nrp + i] = v;
+    }
 }
+
+// 64x64 Cholesky of diagonal block k in shared memory; one CTA per candidate
+__global__ void __launch_bounds__(256) big_potrf_kernel(BigArgs G, int k) {
+    __shared__ double S[64 * 65];
+    __shared__ double s_ri;
+    __shared__ int s_bad;
+    const int b = blockIdx.x, tid = threadIdx.x;
+    double* Ab = G.A + (size_t)b * G.stride + (size_t)(k * 64) * G.nrp + k * 64;
+    for (int e = tid; e < 4096; e += 256) { int r = e % 64, c = e / 64; S[c * 65 + r] = Ab[(size_t)c * G.nrp + r]; }
+    if (tid == 0) s_bad = 0;
+    __syncthreads();
+    double ld = 0.0;
+    for (int j = 0; j < 64; ++j) {
+        if (tid == 0) {
+            const double piv = S[j * 65 + j];
+            const bool live = (k * 64 + j) < G.n;
+            if (live && !(piv > PIVOT_MIN)) s_bad = 1;
+            if (live) ld += log(piv);
+            const double ri = fast_rsqrt(piv);
+            s_ri = ri;
+            S[j * 65 + j] = piv * ri;
+        }
+        __syncthreads();
+        const double ri = s_ri;
+        if (tid > j && tid < 64) S[j * 65 + tid] *= ri;
+        __syncthreads();
+        for (int e = tid; e < 4096; e += 256) {
+            const int r = e % 64, c = e / 64;
+            if (c > j && r >= c) S[c * 65 + r] = fma(-S[j * 65 + r], S[j * 65 + c], S[c * 65 + r]);
+        }
+        __syncthreads();
+    }
+    for (int e = tid; e < 4096; e += 256) { int r = e % 64, c = e / 64; if (r >= c) Ab[(size_t)c * G.nrp + r] = S[c * 65 + r]; }
+    if (tid == 0) {
+        G.logdet[b] += ld;
+        if (s_bad) G.bad[b] = 1;
+    }
+}
+
+// rows of block column k below the diagonal block: X L_kk' = A, one thread per row
+__global__ void __launch_bounds__(64) big_trsm_kernel(BigArgs G, int k) {
+    extern __shared__ __align__(16) double smt[];
+    double* Lk = smt;                   // L_kk(c, c1) at Lk[c1*65 + c]
+    double* Xs = smt + 64 * 65;         // the 64 rows of this CTA, Xs[c*65 + r]
+    const int b = blockIdx.y, rt = blockIdx.x, tid = threadIdx.x;
+    const size_t colk = (size_t)(k * 64) * G.nrp;
+    const double* Ld = G.A + (size_t)b * G.stride + colk + k * 64;
+    double* Ar = G.A + (size_t)b * G.stride + colk + (size_t)(k + 1 + rt) * 64;
+    for (int c = 0; c < 64; ++c) {
+        Lk[c * 65 + tid] = Ld[(size_t)c * G.nrp + tid];
+        Xs[c * 65 + tid] = Ar[(size_t)c * G.nrp + tid];
+    }
+    __syncthreads();
+    for (int c = 0; c < 64; ++c) {
+        double x = Xs[c * 65 + tid];
+        for (int c1 = 0; c1 < c; ++c1) x = fma(-Xs[c1 * 65 + tid], Lk[c1 * 65 + c], x);
+        Xs[c * 65 + tid] = x / Lk[c * 65 + c];
+    }
+    for (int c = 0; c < 64; ++c) Ar[(size_t)c * G.nrp + tid] = Xs[c * 65 + tid];
+}
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// trailing update with panel k: C(ti, tj) -= P_ti P_tj', 64x64 tiles, ti >= tj > k.
+// 128 threads = 4 warps, warp (wr, wc) owns a 32x32 quadrant = 4x4 DMMA m8n8k4 tiles.
+// Panel blocks are staged k-major with leading dimension 72 (k-stride = 64 B mod 128 B) so one
+// fragment load of a warp (8 rows x 4 k) hits every bank exactly once per wavefront.
+__global__ void __launch_bounds__(128) big_syrk_kernel(BigArgs G, int k, int ntile) {
+    extern __shared__ __align__(16) double sm[];
+    double* Pi = sm;                // [64 k][72]
+    double* Pj = sm + 64 * 72;
+    const int b = blockIdx.y;
+    // decode the lower-triangular tile index -> (ti, tj), ti >= tj, both counted from k+1
+    int t = blockIdx.x, tj = 0, rowlen = ntile;      // ntile = row tiles below/at block k+1
+    while (t >= rowlen) { t -= rowlen; ++tj; --rowlen; }
+    const int ti = tj + t;
+    // column tiles only exist while tj is a real block column
+    const int gi = k + 1 + ti, gj = k + 1 + tj;
+    const size_t colk = (size_t)(k * 64) * G.nrp;
+    const double* Ab = G.A + (size_t)b * G.stride;
+    const int tid = threadIdx.x;
+    for (int e = tid; e < 4096; e += 128) {
+        const int r = e % 64, kk = e / 64;
+        Pi[kk * 72 + r] = Ab[colk + (size_t)kk * G.nrp + (size_t)gi * 64 + r];
+        Pj[kk * 72 + r] = Ab[colk + (size_t)kk * G.nrp + (size_t)gj * 64 + r];
+    }
+    __syncthreads();
+    const int warp = tid >> 5, lane = tid & 31;
+    const int wr = (warp >> 1) * 32, wc = (warp & 1) * 32;
+    const int fr = lane >> 2, fk = lane & 3;
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+#pragma unroll 4
+    for (int k0 = 0; k0 < 64; k0 += 4) {
+        double af[4], bf[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) af[i] = Pi[(k0 + fk) * 72 + wr + 8 * i + fr];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) bf[j] = Pj[(k0 + fk) * 72 + wc + 8 * j + fr];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+    }
+    double* C = G.A + (size_t)b * G.stride + (size_t)(gj * 64) * G.nrp + (size_t)gi * 64;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int r = wr + 8 * i + fr, c = wc + 8 * j + 2 * fk;
+            C[(size_t)c * G.nrp + r] -= acc[i][j][0];
+            C[(size_t)(c + 1) * G.nrp + r] -= acc[i][j][1];
+        }
+}
+
+__global__ void __launch_bounds__(256) big_finish_kernel(BigArgs G, int64_t b0, double sigma2, int mean_mode, double tau,
+                                                        double* out_nll, double* out_beta, int32_t* out_status) {
+    __shared__ double red[64];
+    const int b = blockIdx.x, tid = threadIdx.x, n = G.n;
+    const double* Ab = G.A + (size_t)b * G.stride;
+    double s11 = 0.0, s1y = 0.0;
+    for (int kk = tid; kk < n; kk += 256) {
+        const double zy = Ab[(size_t)kk * G.nrp + G.ncp], z1 = Ab[(size_t)kk * G.nrp + G.ncp + 1];
+        s11 = fma(z1, z1, s11);
+        s1y = fma(z1, zy, s1y);
+    }
+    team_sum2<256>(s11, s1y, red);
+    const double beta = s1y / s11;
+    double qr = 0.0, dummy = 0.0;
+    for (int kk = tid; kk < n; kk += 256) {
+        const double zy = Ab[(size_t)kk * G.nrp + G.ncp], z1 = Ab[(size_t)kk * G.nrp + G.ncp + 1];
+        const double rz = fma(-beta, z1, zy);
+        qr = fma(rz, rz, qr);
+    }
+    team_sum2<256>(qr, dummy, red);
+    if (tid == 0) {
+        const double c = G.prm[b].c;
+        const double logdet = G.logdet[b];
+        double nll;
+        if (mean_mode == 0) nll = 0.5 * (qr / c + n * LOG2PI + n * log(c) + logdet);
+        else {
+            const double g = 1.0 + tau * tau * s11 / c;
+            nll = 0.5 * (qr / c + s1y * s1y / (c * s11 * g) + n * LOG2PI + n * log(c) + logdet + log(g));
+        }
+        const bool bad = G.bad[b] || !(nll == nll);
+        const double nanv = __longlong_as_double(0x7ff8000000000000LL);
+        out_nll[b0 + b] = bad ? nanv : nll;
+        if (out_beta) out_beta[b0 + b] = bad ? nanv : beta;
+        if (out_status) out_status[b0 + b] = bad ? 1 : 0;
+    }
+}
+
+inline int bigchol_nll_batch(BigCholWorkspace& ws, cudaStream_t stream, int num_sm, const double* d_X, const double* d_y,
+                             int n, int d, int family, int scale, const double* d_cand, int64_t B, int64_t ldc,
+                             double sigma2, int mean_mode, double tau, double* d_nll, double* d_beta, int32_t* d_status,
+                             int64_t* launches, char* err, size_t errlen) {
+#define BIGCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+        snprintf(err, errlen, "bigchol %s: %s", #call, cudaGetErrorString(e_)); return -2; } } while (0)
+    const int ncp = (n + 63) / 64 * 64, nrp = ncp + 64, T = ncp / 64;
+    const size_t per = (size_t)nrp * ncp * 8;
+    size_t freeb = 0, totalb = 0;
+    BIGCK(cudaMemGetInfo(&freeb, &totalb));
+    size_t budget = std::min<size_t>((freeb + ws.bytesA) / 2, (size_t)24 << 30);
+    int chunk = (int)std::min<int64_t>(B, std::max<size_t>(1, budget / per));
+    if (chunk < 1 || per > budget) { snprintf(err, errlen, "n=%d does not fit in device memory", n); return -3; }
+    if ((size_t)chunk * per > ws.bytesA || chunk > ws.cap) {
+        ws.release();
+        BIGCK(cudaMalloc(&ws.A, (size_t)chunk * per));
+        BIGCK(cudaMalloc(&ws.logdet, (size_t)chunk * 8));
+        BIGCK(cudaMalloc(&ws.bad, (size_t)chunk * 4));
+        BIGCK(cudaMalloc(&ws.prm, (size_t)chunk * sizeof(Prm)));
+        ws.bytesA = (size_t)chunk * per;
+        ws.cap = chunk;
+    }
+    BIGCK(cudaFuncSetAttribute(big_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 64 * 72 * 8));
+    BIGCK(cudaFuncSetAttribute(big_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 64 * 65 * 8));
+    FactorArgs F;
+    memset(&F, 0, sizeof(F));
+    F.d = d; F.cand = d_cand; F.ldc = ldc; F.n_params = B; F.family = family; F.logscale = scale; F.sigma2 = sigma2;
+    F.force_clamp = 1;
+    BigArgs G;
+    G.A = ws.A; G.n = n; G.d = d; G.ncp = ncp; G.nrp = nrp; G.stride = (int64_t)nrp * ncp;
+    G.X = d_X; G.y = d_y; G.prm = ws.prm; G.logdet = ws.logdet; G.bad = ws.bad;
+    for (int64_t b0 = 0; b0 < B; b0 += chunk) {
+        const int nb = (int)std::min<int64_t>(chunk, B - b0);
+        big_params_kernel<<<(nb + 127) / 128, 128, 0, stream>>>(F, b0, nb, ws.prm, ws.logdet, ws.bad);
+        big_build_kernel<<<dim3(T, T + 1, nb), 256, 0, stream>>>(G);
+        *launches += 2;
+        for (int k = 0; k < T; ++k) {
+            big_potrf_kernel<<<nb, 256, 0, stream>>>(G, k);
+            const int rt = (nrp - (k + 1) * 64) / 64;           // row tiles below the diagonal block
+            if (rt > 0) big_trsm_kernel<<<dim3(rt, nb), 64, 2 * 64 * 65 * 8, stream>>>(G, k);
+            *launches += 2;
+            const int ct = T - (k + 1);                         // real block columns still to update
+            if (ct > 0) {
+                // tiles (ti, tj) with tj < ct, ti in [tj, rt): sum_{tj<ct} (rt - tj)
+                const int ntiles = ct * rt - ct * (ct - 1) / 2;
+                big_syrk_kernel<<<dim3(ntiles, nb), 128, 2 * 64 * 72 * 8, stream>>>(G, k, rt);
+                *launches += 1;
+            }
+        }
+        big_finish_kernel<<<nb, 256, 0, stream>>>(G, b0, sigma2, mean_mode, tau, d_nll, d_beta, d_status);
+        *launches += 1;
+        BIGCK(cudaGetLastError());
+    }
+#undef BIGCK
+    return 0;
+}
+
+}  // namespace ccgp

@@ -1,0 +1,134 @@
+/* ccgp_shim.c -- .Call entry points that bind the reference R scripts to libccgp.so.
+ *
+ * Build (where R exists; R is NOT in the build container, so this file is compile-checked
+ * only on a machine with R):
+ *     R CMD SHLIB ccgp_shim.c -I../include -L../convex-combination-of-gaussian-processes_b200/lib -lccgp
+ *
+ * Conventions: REALSXP matrices are column-major doubles and are handed to libccgp as they
+ * are (no copy); INTSXP is int32.  The context handle is an external pointer with a C
+ * finalizer.  libccgp never calls back into R and returns an int status, so Rf_error() is
+ * only raised here, after every temporary has been PROTECTed/released (Rf_error longjmps).
+ * Per-candidate numerical failure is not an error: the value comes back NaN with status 1
+ * and r/ccgp.R turns it into NA, reproducing `try(solve(R))` -> NA at [A]:448-449.
+ */
+#include <R.h>
+#include <Rinternals.h>
+#include <stdint.h>
+#include "ccgp.h"
+
+static void ctx_finalizer(SEXP ptr) {
+    ccgp_ctx* ctx = (ccgp_ctx*)R_ExternalPtrAddr(ptr);
+    if (ctx) { ccgp_destroy(ctx); R_ClearExternalPtr(ptr); }
+}
+
+static ccgp_ctx* get_ctx(SEXP ptr) {
+    ccgp_ctx* ctx = (ccgp_ctx*)R_ExternalPtrAddr(ptr);
+    if (!ctx) Rf_error("ccgp: context already destroyed");
+    return ctx;
+}
+
+static void check(ccgp_ctx* ctx, int rc, const char* what) {
+    if (rc != CCGP_OK) Rf_error("ccgp %s failed (%d): %s", what, rc, ccgp_last_error(ctx));
+}
+
+SEXP ccgp_R_create(SEXP device) {
+    ccgp_ctx* ctx = NULL;
+    int rc = ccgp_create(&ctx, Rf_asInteger(device));
+    if (rc != CCGP_OK) Rf_error("ccgp_create failed (%d): %s", rc, ccgp_last_error(NULL));
+    SEXP ptr = PROTECT(R_MakeExternalPtr(ctx, R_NilValue, R_NilValue));
+    R_RegisterCFinalizerEx(ptr, ctx_finalizer, TRUE);
+    UNPROTECT(1);
+    return ptr;
+}
+
+/* D.train (n x d), y (n) */
+SEXP ccgp_R_set_design(SEXP ptr, SEXP X, SEXP y) {
+    ccgp_ctx* ctx = get_ctx(ptr);
+    if (!Rf_isMatrix(X) || !Rf_isReal(X) || !Rf_isReal(y)) Rf_error("ccgp: D.train must be a double matrix, y a double vector");
+    int n = Rf_nrows(X), d = Rf_ncols(X);
+    if (XLENGTH(y) != n) Rf_error("ccgp: length(y) != nrow(D.train)");
+    check(ctx, ccgp_set_design(ctx, REAL(X), n, d, REAL(y)), "set_design");
+    return R_NilValue;
+}
+
+/* cand: B x k matrix.  Returns list(nll, beta, status). */
+SEXP ccgp_R_nll_batch(SEXP ptr, SEXP family, SEXP scale, SEXP cand, SEXP sigma2, SEXP mean_mode, SEXP tau) {
+    ccgp_ctx* ctx = get_ctx(ptr);
+    if (!Rf_isMatrix(cand) || !Rf_isReal(cand)) Rf_error("ccgp: candidates must be a double matrix");
+    int64_t B = Rf_nrows(cand);
+    SEXP nll = PROTECT(Rf_allocVector(REALSXP, B));
+    SEXP beta = PROTECT(Rf_allocVector(REALSXP, B));
+    SEXP status = PROTECT(Rf_allocVector(INTSXP, B));
+    int rc = ccgp_nll_batch(ctx, Rf_asInteger(family), Rf_asInteger(scale), REAL(cand), B, B, Rf_asReal(sigma2),
+                            Rf_asInteger(mean_mode), Rf_asReal(tau), REAL(nll), REAL(beta), (int32_t*)INTEGER(status));
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 3));
+    SET_VECTOR_ELT(out, 0, nll); SET_VECTOR_ELT(out, 1, beta); SET_VECTOR_ELT(out, 2, status);
+    UNPROTECT(4);
+    check(ctx, rc, "nll_batch");
+    return out;
+}
+
+/* Returns list(Rinv (n x n x B array), beta, status). */
+SEXP ccgp_R_rinv_batch(SEXP ptr, SEXP family, SEXP scale, SEXP cand, SEXP n_) {
+    ccgp_ctx* ctx = get_ctx(ptr);
+    int64_t B = Rf_nrows(cand);
+    int n = Rf_asInteger(n_);
+    SEXP rinv = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)n * n * B));
+    SEXP beta = PROTECT(Rf_allocVector(REALSXP, B));
+    SEXP status = PROTECT(Rf_allocVector(INTSXP, B));
+    int rc = ccgp_rinv_batch(ctx, Rf_asInteger(family), Rf_asInteger(scale), REAL(cand), B, B, REAL(rinv), REAL(beta),
+                             (int32_t*)INTEGER(status));
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 3));
+    SET_VECTOR_ELT(out, 0, rinv); SET_VECTOR_ELT(out, 1, beta); SET_VECTOR_ELT(out, 2, status);
+    UNPROTECT(4);
+    check(ctx, rc, "rinv_batch");
+    return out;
+}
+
+/* pars: S x k, pars_vec: S x k' or NULL, Xnew: T x d.  Returns list(mean (T x S), var (T x S), status). */
+SEXP ccgp_R_predict(SEXP ptr, SEXP family, SEXP pars, SEXP vec_family, SEXP pars_vec, SEXP Xnew, SEXP sigma2) {
+    ccgp_ctx* ctx = get_ctx(ptr);
+    int64_t S = Rf_nrows(pars), T = Rf_nrows(Xnew);
+    SEXP mean = PROTECT(Rf_allocMatrix(REALSXP, (int)T, (int)S));
+    SEXP var = PROTECT(Rf_allocMatrix(REALSXP, (int)T, (int)S));
+    SEXP status = PROTECT(Rf_allocVector(INTSXP, S));
+    const double* pv = Rf_isNull(pars_vec) ? NULL : REAL(pars_vec);
+    int rc = ccgp_predict(ctx, Rf_asInteger(family), REAL(pars), S, S, Rf_asInteger(vec_family), pv, S, REAL(Xnew), T,
+                          Rf_asReal(sigma2), REAL(mean), REAL(var), (int32_t*)INTEGER(status));
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 3));
+    SET_VECTOR_ELT(out, 0, mean); SET_VECTOR_ELT(out, 1, var); SET_VECTOR_ELT(out, 2, status);
+    UNPROTECT(4);
+    check(ctx, rc, "predict");
+    return out;
+}
+
+/* D.old: n_old x d (or NULL), D.new: (n_new*d) x C matrix whose columns are c(D.new) vectors,
+ * params: P x 3.  Returns list(negdet (C x P), logdet (C x P), status (C x P)). */
+SEXP ccgp_R_me_schur_batch(SEXP ptr, SEXP D_old, SEXP D_new, SEXP n_new_, SEXP d_, SEXP params) {
+    ccgp_ctx* ctx = get_ctx(ptr);
+    int n_new = Rf_asInteger(n_new_), d = Rf_asInteger(d_);
+    int n_old = Rf_isNull(D_old) ? 0 : Rf_nrows(D_old);
+    int64_t C = Rf_ncols(D_new), P = Rf_nrows(params);
+    SEXP negdet = PROTECT(Rf_allocMatrix(REALSXP, (int)C, (int)P));
+    SEXP logdet = PROTECT(Rf_allocMatrix(REALSXP, (int)C, (int)P));
+    SEXP status = PROTECT(Rf_allocMatrix(INTSXP, (int)C, (int)P));
+    int rc = ccgp_me_schur_batch(ctx, n_old ? REAL(D_old) : NULL, n_old, d, REAL(D_new), n_new, C, REAL(params), P, P,
+                                 REAL(negdet), REAL(logdet), (int32_t*)INTEGER(status));
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 3));
+    SET_VECTOR_ELT(out, 0, negdet); SET_VECTOR_ELT(out, 1, logdet); SET_VECTOR_ELT(out, 2, status);
+    UNPROTECT(4);
+    check(ctx, rc, "me_schur_batch");
+    return out;
+}
+
+/* Mixed correlation block between the rows of A and of B (B = NULL: A with itself). */
+SEXP ccgp_R_mixed_corr(SEXP ptr, SEXP family, SEXP params, SEXP A, SEXP B) {
+    ccgp_ctx* ctx = get_ctx(ptr);
+    int na = Rf_nrows(A), d = Rf_ncols(A);
+    int nb = Rf_isNull(B) ? na : Rf_nrows(B);
+    SEXP out = PROTECT(Rf_allocMatrix(REALSXP, na, nb));
+    int rc = ccgp_mixed_corr(ctx, Rf_asInteger(family), REAL(params), REAL(A), na, Rf_isNull(B) ? NULL : REAL(B), nb, d, REAL(out));
+    UNPROTECT(1);
+    check(ctx, rc, "mixed_corr");
+    return out;
+}

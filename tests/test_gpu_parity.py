@@ -338,3 +338,43 @@ def test_subset_logdets(engine, golden):
         got, st = engine.subset_logdet_batch(pool, golden["sub_idx_%d" % m], GAUSS_ANISO_LAMBDA, par)
         assert np.all(st == 0)
         assert np.abs(got - golden["sub_logdet_%d" % m]).max() < 1e-9
+
+
+# ---------------------------------------------------------------- blocked large-n path
+def test_blocked_path_matches_shared_memory_path(engine, golden, designs):
+    """CCGP_FORCE_BIG routes n=100 through the HBM-resident blocked Cholesky (DMMA trailing update)."""
+    engine.set_design(designs["maximin100"], golden["c1n100_y"])
+    os.environ["CCGP_FORCE_BIG"] = "1"
+    try:
+        nll, beta, st = engine.nll_batch(golden["c1n100_nat"], GAUSS_ANISO_LAMBDA, 1.0)
+        nll_t, _, _ = engine.nll_batch(golden["c1n100_nat"][:8], GAUSS_ANISO_LAMBDA, 1.0, mean_mode=MEAN_ZERO_PLUS_TAU2, tau=10.0)
+    finally:
+        os.environ.pop("CCGP_FORCE_BIG", None)
+    assert np.all(st == 0)
+    assert rel_err(-nll, golden["c1n100_ref"]).max() < TOL
+    assert rel_err(beta, golden["c1n100_beta"]).max() < TOL
+    ref_t, _, _ = engine.nll_batch(golden["c1n100_nat"][:8], GAUSS_ANISO_LAMBDA, 1.0, mean_mode=MEAN_ZERO_PLUS_TAU2, tau=10.0)
+    assert rel_err(nll_t, ref_t).max() < 1e-12
+
+
+@pytest.mark.parametrize("n", [300, 2048])
+def test_large_n_vs_oracle(engine, n):
+    """SURVEY 8d ME-B(1) shape: synthetic LHS on [-1,1]^2, anisotropic, lambda-family.  The survey's
+    theta = (30, 60) makes a 2048-point Gaussian Gram matrix numerically singular (kappa >> 1e16), so the
+    scales are tied to the point spacing h ~ 2/sqrt(n) to keep kappa_1(R) inside the stated parity range."""
+    X = workloads.synthetic_pool(n, seed=2048)
+    rng = np.random.default_rng(3)
+    y = np.sin(3 * X[:, 0]) * np.cos(2 * X[:, 1]) + 0.05 * rng.normal(size=n)
+    h2 = 4.0 / n
+    nat = np.array([[0.5, 1.5 / h2, 2.5 / h2, 2.0], [0.3, 2.0 / h2, 1.6 / h2, 1.0], [0.8, 1.2 / h2, 3.0 / h2, 0.5]])
+    engine.set_design(X, y)
+    nll, beta, st = engine.nll_batch(nat, GAUSS_ANISO_LAMBDA, 1.3)
+    assert np.all(st == 0)
+    for b in range(3 if n <= 300 else 1):
+        kappa = orc.cond1(orc.Mixed_corr_matrix_direct(X, orc.FAMILY_ANISO_LAMBDA, nat[b]))
+        assert kappa < 1e6, kappa
+        o = orc.loglik_reference(X, y, 1.3, orc.FAMILY_ANISO_LAMBDA, nat[b])
+        m = orc.loglik_minimal(X, y, 1.3, orc.FAMILY_ANISO_LAMBDA, nat[b])
+        assert rel_err(-nll[b], m["loglik"]) < TOL
+        assert rel_err(-nll[b], o["loglik"]) < TOL
+        assert rel_err(beta[b], m["beta"]) < 1e-9
