@@ -76,8 +76,8 @@ struct Variant { int team, tr, tc, minb; factor_fn fn_d0, fn_d2; };
 
 #define CCGP_VARIANTS(X)                                                                           \
     X(32, 4, 4, 16) X(32, 8, 4, 16) X(64, 4, 4, 8) X(64, 8, 4, 8) X(64, 4, 8, 8) X(128, 4, 4, 4)      \
-    X(128, 8, 4, 4) X(128, 4, 8, 4) X(256, 4, 4, 4) X(256, 4, 4, 2) X(256, 4, 8, 2) X(192, 4, 4, 4)   \
-    X(160, 4, 4, 4) X(96, 4, 4, 5) X(224, 4, 4, 4) X(192, 4, 8, 4)
+    X(128, 8, 4, 4) X(128, 4, 8, 4) X(256, 4, 4, 4) X(256, 4, 4, 2) X(32, 8, 4, 4) X(32, 4, 4, 4)   \
+    X(32, 8, 8, 4) X(96, 4, 4, 5) X(64, 8, 4, 4) X(128, 4, 4, 5)
 
 #define X(T, R, K, M) {T, R, K, M, factor_kernel<T, R, K, 0, M>, factor_kernel<T, R, K, 2, M>},
 static const Variant g_variants[] = {CCGP_VARIANTS(X)};
@@ -87,8 +87,7 @@ static const int g_num_variants = sizeof(g_variants) / sizeof(g_variants[0]);
 static int default_variant(const Layout& l) {
     // measured on B200 (profiles/r01_tune_variants_v3.json): one warp per candidate wins while many
     // CTAs fit per SM; 4 warps once shared memory caps residency at ~4 candidates per SM
-    if (l.npad <= 56) return 0;    // 32 threads, 4x4 tiles
-    if (l.npad <= 72) return 2;    // 64 threads, 4x4 tiles
+    if (l.npad <= 72) return 0;    // 32 threads, 4x4 tiles
     if (l.npad <= 136) return 5;   // 128 threads, 4x4 tiles
     return 9;                      // 256 threads, 4x4 tiles (1-2 candidates resident per SM)
 }
@@ -167,6 +166,8 @@ static int launch_factor(ccgp_ctx* ctx, FactorArgs& A) {
     if (grid > A.W) grid = A.W;
     if (grid < 1) return 0;
     A.dbg = ctx->dbg;
+    A.num_sm = env_int("CCGP_NO_ROTATE", 0) ? 0 : ctx->num_sm;
+    A.debug_stop = env_int("CCGP_DEBUG_STOP", 0);
     RC(get_tiletab(ctx, l, var.tr, var.tc, &A.tiletab));
     fn<<<(unsigned)grid, var.team, smem, ctx->stream>>>(A);
     CK(cudaGetLastError());

@@ -112,8 +112,11 @@ struct FactorArgs {
     int64_t W;            // work items: w -> design w % n_designs, parameter row w / n_designs
     double span2[MAXD];   // squared coordinate ranges of the design (bounds the exponents)
     int force_clamp;      // 1 when span2 is unknown (per-candidate designs)
+    int num_sm;               // CTAs co-resident on one SM are blockIdx = s, s+num_sm, ..: each takes a
+                              // different warp for the serial diagonal block (spreads it over the SMSPs)
     const uint32_t* tiletab;  // [NJ+1] first-tile index per block column, then one packed
                               // (first row | row-pair stride << 10 | first column << 20) per tile
+    int debug_stop;       // debug: 1 = stop after the build phase (tools/occupancy_probe.py)
     long long* dbg;       // optional phase-timing buffer (tools/phase_timing.py); NULL in production
     double* out0;         // NLL: nll          DET: log det (all pivots)
     double* out1;         // NLL: beta         DET: log det (tail pivots)
@@ -214,50 +217,61 @@ __device__ __forceinline__ void build_panel(const FactorArgs& A, double* Ls, con
 #pragma unroll
         for (int k = 0; k < DT; ++k) wts[k] = prm->wts[k];
     }
-    for (int c = gw; c < 8; c += gnw) {
+    // a warp takes two adjacent columns at a time: the row point is loaded once and four
+    // exponentials (2 components x 2 columns) are in flight per lane
+    for (int c = 2 * gw; c < 8; c += 2 * gnw) {
         const int j = 8 * J + c;
-        double* col = pan + c * H;
-        if (j >= n) {                                    // dead column (warp-uniform)
-            for (int r0 = lane; r0 < H; r0 += 32) col[r0] = 0.0;
+        double* col0 = pan + c * H;
+        double* col1 = col0 + H;
+        if (j >= n) {                                    // both columns dead (warp-uniform)
+            for (int r0 = lane; r0 < H; r0 += 32) { col0[r0] = 0.0; col1[r0] = 0.0; }
             continue;
         }
-        double xj[DT > 0 ? DT : 1];
+        const bool live1 = (j + 1) < n;
+        const int j1 = live1 ? j + 1 : j;
+        double xj0[DT > 0 ? DT : 1], xj1[DT > 0 ? DT : 1];
         if (DT > 0) {
 #pragma unroll
-            for (int k = 0; k < DT; ++k) xj[k] = Xs[k * npx + j];
+            for (int k = 0; k < DT; ++k) { xj0[k] = Xs[k * npx + j]; xj1[k] = Xs[k * npx + j1]; }
         }
-        // two rows per iteration (passes u and u + half) keep four exponentials in flight
-        const int P = (H + 31) >> 5, half = (P + 1) >> 1;
-        for (int u = 0; u < half; ++u) {
-            const int ra = lane + 32 * u, rb = ra + 32 * half;
-            const int ia = 8 * J + ra, ib = 8 * J + rb;
-            const bool two = (u + half < P);                          // warp-uniform
-            const int ica = min(ia, n - 1), icb = min(ib, n - 1);     // rows >= n are fixed up below
-            double s1a = 0.0, s1b = 0.0;
+        // entries (row r0, columns j and j+1) of the panel
+        auto entry2 = [&](int r0, double& v0, double& v1) {
+            const int i = 8 * J + r0;
+            const int ic = min(i, n - 1);                // rows >= n are fixed up below
+            double s0 = 0.0, s1 = 0.0;
             if (DT > 0) {
 #pragma unroll
                 for (int k = 0; k < DT; ++k) {
-                    double da = Xs[k * npx + ica] - xj[k], db = Xs[k * npx + icb] - xj[k];
-                    s1a = fma(wts[k] * da, da, s1a);
-                    s1b = fma(wts[k] * db, db, s1b);
+                    const double xi = Xs[k * npx + ic];
+                    const double d0 = xi - xj0[k], d1 = xi - xj1[k];
+                    s0 = fma(wts[k] * d0, d0, s0);
+                    s1 = fma(wts[k] * d1, d1, s1);
                 }
             } else {
                 for (int k = 0; k < d; ++k) {
-                    const double xjk = Xs[k * npx + j], wk = prm->wts[k];
-                    double da = Xs[k * npx + ica] - xjk, db = Xs[k * npx + icb] - xjk;
-                    s1a = fma(wk * da, da, s1a);
-                    s1b = fma(wk * db, db, s1b);
+                    const double xi = Xs[k * npx + ic], wk = prm->wts[k];
+                    const double d0 = xi - Xs[k * npx + j], d1 = xi - Xs[k * npx + j1];
+                    s0 = fma(wk * d0, d0, s0);
+                    s1 = fma(wk * d1, d1, s1);
                 }
             }
-            double va = fma(b, dexp_neg_dev<CLAMP>(rho * s1a), a * dexp_neg_dev<CLAMP>(s1a));
-            if (ra <= c) va = (ra == c) ? 1.0 : 0.0;   // diagonal corner: unit diagonal, unused upper part
-            if (ia >= n) va = (naug && ia == n) ? ys[j] : ((naug && ia == n + 1) ? 1.0 : 0.0);
-            if (ra < H) col[ra] = va;
-            if (two) {
-                double vb = fma(b, dexp_neg_dev<CLAMP>(rho * s1b), a * dexp_neg_dev<CLAMP>(s1b));
-                if (ib >= n) vb = (naug && ib == n) ? ys[j] : ((naug && ib == n + 1) ? 1.0 : 0.0);
-                if (rb < H) col[rb] = vb;
+            v0 = fma(b, dexp_neg_dev<CLAMP>(rho * s0), a * dexp_neg_dev<CLAMP>(s0));
+            v1 = fma(b, dexp_neg_dev<CLAMP>(rho * s1), a * dexp_neg_dev<CLAMP>(s1));
+            if (r0 <= c + 1) {                           // diagonal corner: unit diagonal, unused upper part
+                if (r0 <= c) v0 = (r0 == c) ? 1.0 : 0.0;
+                v1 = (r0 == c + 1) ? 1.0 : 0.0;
             }
+            if (i >= n) {                                // rows y' and 1', zero padding
+                v0 = (naug && i == n) ? ys[j] : ((naug && i == n + 1) ? 1.0 : 0.0);
+                v1 = (naug && i == n) ? ys[j1] : ((naug && i == n + 1) ? 1.0 : 0.0);
+            }
+            if (!live1) v1 = 0.0;
+        };
+        for (int r0 = lane; r0 < H; r0 += 32) {
+            double v0, v1;
+            entry2(r0, v0, v1);
+            col0[r0] = v0;
+            col1[r0] = v1;
         }
     }
 }
@@ -313,41 +327,50 @@ __device__ __forceinline__ void tile_update(double* Ls, int npad, int J, int ia,
             *reinterpret_cast<double2*>(cb + cc * HC + m * rs) = make_double2(acc[2 * m][cc], acc[2 * m + 1][cc]);
 }
 
-// ---- 8x8 diagonal block of panel J: warp-level, lane r <-> row r (lanes >= 8 mirror) ---------
-// Per column the critical chain is one shuffle (the pivot), one rsqrt, one multiply and one FMA
-// (each row keeps its own diagonal entry `dg` current so the next pivot needs no second shuffle).
+// ---- 8x8 diagonal block of panel J, one warp ---------------------------------------------------
+// Every lane redundantly factors the whole block in registers (36 entries, fully unrolled): no
+// shuffles, ~200 FP64 instructions in the warp's instruction stream instead of ~560 with a
+// lane-per-row layout -- under 4-CTA contention the serial part is bound by how many instructions
+// the warp must issue, not only by the rsqrt/FMA chain.  Per column the chain is
+// rsqrt -> multiply -> FMA (next pivot); everything else fills the issue slots in between.
 __device__ __forceinline__ void diag_block(const FactorArgs& A, double* Ls, double* rinv_s, int J, int lane,
                                            FactorResult& res) {
     const int n = A.lay.n, npad = A.lay.npad;
-    const int H = npad - 8 * J, pbase = blk_base(J, npad);
-    const int r = lane & 7;
-    double a8[8];
+    const int H = npad - 8 * J;
+    double* blk = Ls + blk_base(J, npad);          // entry (r, c) at blk[c*H + r]
+    double a[8][8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) a8[c] = Ls[pbase + c * H + r];
-    double dg = Ls[pbase + r * H + r];
+    for (int c = 0; c < 8; ++c) {
+#pragma unroll
+        for (int r2 = c & ~1; r2 < 8; r2 += 2) {   // rows in aligned pairs; (c-1, c) only adds an unused upper entry
+            double2 v = ld2(blk + c * H + r2);
+            a[r2][c] = v.x; a[r2 + 1][c] = v.y;
+        }
+    }
     double pv_own = 1.0;                     // lane 8+c keeps pivot c for the determinant
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-        const double piv = __shfl_sync(0xffffffffu, dg, c);
+        const double piv = a[c][c];
         const bool live = (8 * J + c) < n;
         const double ri = live ? fast_rsqrt(piv) : 0.0;
         if (live && !(piv > PIVOT_MIN)) res.bad = 1;
         if (live && lane == c + 8) pv_own = piv;
-        double l = a8[c] * ri;
-        if (r > c) dg = fma(-l, l, dg);
-        if (r == c) l = piv * ri;
-        a8[c] = l;
-        double lc2[8];
+        a[c][c] = piv * ri;
 #pragma unroll
-        for (int c2 = c + 1; c2 < 8; ++c2) lc2[c2] = __shfl_sync(0xffffffffu, l, c2);
+        for (int r = c + 1; r < 8; ++r) a[r][c] *= ri;
 #pragma unroll
-        for (int c2 = c + 1; c2 < 8; ++c2) a8[c2] = fma(-l, lc2[c2], a8[c2]);
-        if (lane == 0) rinv_s[c] = ri;
+        for (int c2 = c + 1; c2 < 8; ++c2)
+#pragma unroll
+            for (int r = c2; r < 8; ++r) a[r][c2] = fma(-a[r][c], a[c2][c], a[r][c2]);
+        if (lane == c) rinv_s[c] = ri;
     }
-    if (lane < 8) {
+    if (lane < 8) {                          // lane c writes column c back (rows c..7)
 #pragma unroll
         for (int c = 0; c < 8; ++c)
-            if (c <= r) Ls[pbase + c * H + r] = a8[c];
+            if (lane == c) {
+#pragma unroll
+                for (int r = c; r < 8; ++r) blk[c * H + r] = a[r][c];
+            }
     }
     // determinant bookkeeping off the critical chain: lane 8+c folds pivot c into its own running
     // (mantissa, exponent) pair; the 8 partial products are combined once per candidate
@@ -382,7 +405,8 @@ __device__ __forceinline__ void panel_trsm(double* Ls, const double* rinv_s, int
 // call this.  `ctr` is one shared int (dynamic tile counter).
 template <int TEAM, int TR, int TC, int DT>
 __device__ __forceinline__ FactorResult factor_candidate(const FactorArgs& A, double* Ls, const double* Xs,
-                                                         const double* ys, double* rinv_s, const Prm* prm, int* ctr) {
+                                                         const double* ys, double* rinv_s, const Prm* prm, int* ctr,
+                                                         int fw) {
     static_assert(TR == 4 || TR == 8, "TR");
     static_assert(TC == 4 || TC == 8, "TC");
     constexpr int W = TEAM / 32;
@@ -395,8 +419,9 @@ __device__ __forceinline__ FactorResult factor_candidate(const FactorArgs& A, do
     const int ntiles = (int)__ldg(first + NJ);
 
     CCGP_T0();
+    if (tid == 0) ctr[1] = 0;           // "diagonal block of panel ctr[1] is published"
     const bool clampx = prm->clamp != 0;
-    for (int J = 0; J < NJ; ++J) {
+    for (int J = 0; J < NJ && A.debug_stop != 2; ++J) {
         if (clampx) build_panel<DT, true>(A, Ls, Xs, ys, prm, J, tid, TEAM);
         else build_panel<DT, false>(A, Ls, Xs, ys, prm, J, tid, TEAM);
     }
@@ -406,8 +431,9 @@ __device__ __forceinline__ FactorResult factor_candidate(const FactorArgs& A, do
 
     FactorResult res;
     res.mant_all = 1.0; res.mant_tail = 1.0; res.es_all = 0; res.es_tail = 0; res.bad = 0;
+    if (A.debug_stop >= 1) return res;
 
-    if (warp == 0) diag_block(A, Ls, rinv_s, 0, lane, res);
+    if (warp == fw) diag_block(A, Ls, rinv_s, 0, lane, res);
     team_sync<TEAM>();
     panel_trsm<TEAM>(Ls, rinv_s, npad, 0, tid);
     CCGP_TW(3);
@@ -426,8 +452,15 @@ __device__ __forceinline__ FactorResult factor_candidate(const FactorArgs& A, do
         team_sync<TEAM>();
         CCGP_TB(1);
         // ---- lookahead: warp 0 factors the diagonal block of panel J+1 while the others apply
-        //      panel J to the rest of the trailing matrix; warp 0 joins when it is done ---------
-        if (warp == 0) diag_block(A, Ls, rinv_s, J + 1, lane, res);
+        //      panel J to the rest of the trailing matrix; warp 0 joins when it is done.  The rows
+        //      of panel J+1 are solved in the same phase as soon as the diagonal block is published
+        //      (flag in shared memory), so a step costs two team barriers.
+        if (warp == fw) {
+            diag_block(A, Ls, rinv_s, J + 1, lane, res);
+            __syncwarp();
+            if (W > 1 && lane == 0) { __threadfence_block(); *reinterpret_cast<volatile int*>(ctr + 1) = J + 1; }
+            CCGP_TW(4);
+        }
         for (;;) {
             int base = 0;
             if (lane == 0) base = atomicAdd(ctr, 32);
@@ -440,7 +473,11 @@ __device__ __forceinline__ FactorResult factor_candidate(const FactorArgs& A, do
             }
         }
         CCGP_TW(2);
-        team_sync<TEAM>();
+        if (W > 1 && warp != fw) {
+            while (*reinterpret_cast<volatile int*>(ctr + 1) < J + 1) { }
+            __threadfence_block();
+        }
+        __syncwarp();
         CCGP_TB(2);
         // ---- rows of panel J+1 below its diagonal block ---------------------------------------
         panel_trsm<TEAM>(Ls, rinv_s, npad, J + 1, tid);
@@ -448,7 +485,7 @@ __device__ __forceinline__ FactorResult factor_candidate(const FactorArgs& A, do
         team_sync<TEAM>();
         CCGP_TB(3);
     }
-    if (warp == 0) {
+    if (warp == fw) {
         // fold the 8 per-column partial products (lanes 8..15) into lane 0, in a fixed order
         res.bad = __any_sync(0xffffffffu, res.bad) ? 1 : 0;
         double ma = 1.0, mt = 1.0;
@@ -523,6 +560,8 @@ __global__ void __launch_bounds__(TEAM, MINB) factor_kernel(const FactorArgs A) 
     int* ctr = reinterpret_cast<int*>(reinterpret_cast<char*>(prm) + sizeof(Prm));
     const int tid = threadIdx.x;
     const int n = lay.n, npad = lay.npad;
+    const int fw = (A.num_sm > 0 ? (int)(blockIdx.x / A.num_sm) : 0) % (TEAM / 32);   // warp of the serial part
+    const int otid = fw * 32;                                                        // its lane 0 writes the outputs
 
     if (A.design_mode == DESIGN_SHARED) {
         for (int e = tid; e < n * A.d; e += TEAM) {
@@ -540,7 +579,7 @@ __global__ void __launch_bounds__(TEAM, MINB) factor_kernel(const FactorArgs A) 
         if (A.design_mode != DESIGN_SHARED) stage_design<TEAM>(A, dsg, Xs);
         team_sync<TEAM>();
 
-        FactorResult res = factor_candidate<TEAM, TR, TC, DT>(A, Ls, Xs, ys, rinv_s, prm, ctr);
+        FactorResult res = factor_candidate<TEAM, TR, TC, DT>(A, Ls, Xs, ys, rinv_s, prm, ctr, fw);
 
         if (A.out_mode == OUT_NLL) {
             double s11 = 0.0, s1y = 0.0;
@@ -559,7 +598,7 @@ __global__ void __launch_bounds__(TEAM, MINB) factor_kernel(const FactorArgs A) 
                 qr = fma(rz, rz, qr);
             }
             team_sum2<TEAM>(qr, dummy, red);
-            if (tid == 0) {
+            if (tid == otid) {
                 const double c = prm->c;
                 const double logdet = log(res.mant_all) + res.es_all * LN2;
                 double nll;
@@ -577,7 +616,7 @@ __global__ void __launch_bounds__(TEAM, MINB) factor_kernel(const FactorArgs A) 
                 if (A.status) A.status[w] = bad ? 1 : 0;
             }
         } else {
-            if (tid == 0) {
+            if (tid == otid) {
                 const double nanv = __longlong_as_double(0x7ff8000000000000LL);
                 const bool bad = res.bad != 0;
                 if (A.out0) A.out0[w] = bad ? nanv : log(res.mant_all) + res.es_all * LN2;

@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(TEAM, MINB) predict_kernel(const PredictArgs P
             }
         }
         __syncthreads();
-        FactorResult res = factor_candidate<TEAM, TR, TC, DT>(A, Ls, Xs, ys, rinv_s, prm, reinterpret_cast<int*>(reinterpret_cast<char*>(prm) + sizeof(Prm)));
+        FactorResult res = factor_candidate<TEAM, TR, TC, DT>(A, Ls, Xs, ys, rinv_s, prm, reinterpret_cast<int*>(reinterpret_cast<char*>(prm) + sizeof(Prm)), 0);
         if (tid == 0) red[62] = res.bad ? 1.0 : 0.0;
 
         double s11 = 0.0, s1y = 0.0;
@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(TEAM, MINB) rinv_kernel(const RinvArgs P) {
         __syncthreads();
         if (tid == 0) load_params(A, s, prm);
         __syncthreads();
-        FactorResult res = factor_candidate<TEAM, TR, TC, 0>(A, Ls, Xs, ys, rinv_s, prm, reinterpret_cast<int*>(reinterpret_cast<char*>(prm) + sizeof(Prm)));
+        FactorResult res = factor_candidate<TEAM, TR, TC, 0>(A, Ls, Xs, ys, rinv_s, prm, reinterpret_cast<int*>(reinterpret_cast<char*>(prm) + sizeof(Prm)), 0);
         if (tid == 0) red[62] = res.bad ? 1.0 : 0.0;
         double s11 = 0.0, s1y = 0.0;
         for (int k = tid; k < n; k += TEAM) {

@@ -24,7 +24,7 @@ eng.nll_batch(th, GAUSS_ANISO_LAMBDA, s2, scale=LOGSCALE)
 eng._lib.ccgp_debug_phase_timing(eng._h, 0, C.cast(buf, C.c_void_p))
 cfg = eng.last_nll_config()
 ncand = B / (148 * cfg["ctas_per_sm"])
-names = ["build0", "A:kloop", "B:diag|build", "C:trsm"]
+names = ["build", "U1", "lookahead(tiles)+wait", "trsm", "diag block (warp 0)"]
 print("variant", cfg, "candidates per CTA ~ %.1f" % ncand)
 for w in (0, 1):
     tot = 0
