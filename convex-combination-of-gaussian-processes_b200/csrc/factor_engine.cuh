@@ -82,10 +82,39 @@ inline Layout make_layout(int n, int naug) {
     return l;
 }
 
-// shared bytes: L | Xs[d*npx] | ys[npx] | rinv[8] | red[64] | Prm | ints[4]
+// shared bytes: L | Xs[d*npx] | ys[npx] | rinv[8] | red[64] | Prm | ints[4] | tile table
+// (the table has NJ+1 + total/(TR*TC) <= NJ+1 + total/16 entries)
+__host__ __device__ __forceinline__ size_t tiletab_bytes(const Layout& l) { return ((size_t)l.NJ + 1 + l.total / 16 + 3) / 4 * 16; }
 inline size_t smem_bytes(const Layout& l, int d) {
     size_t dbl = (size_t)l.total + (size_t)d * l.npx + l.npx + 8 + 64;
-    return dbl * 8 + sizeof(Prm) + 16;
+    return dbl * 8 + sizeof(Prm) + 16 + tiletab_bytes(l);
+}
+
+struct SmemPtrs {
+    double *Ls, *Xs, *ys, *rinv_s, *red;
+    Prm* prm;
+    int* ctr;
+    uint32_t* tab;
+    char* end;     // first byte after the factor engine's block (kernels with extra buffers start here)
+};
+__device__ __forceinline__ SmemPtrs carve_smem(double* smem, const Layout& lay, int d) {
+    SmemPtrs p;
+    p.Ls = smem;
+    p.Xs = p.Ls + lay.total;
+    p.ys = p.Xs + d * lay.npx;
+    p.rinv_s = p.ys + lay.npx;
+    p.red = p.rinv_s + 8;
+    p.prm = reinterpret_cast<Prm*>(p.red + 64);
+    p.ctr = reinterpret_cast<int*>(reinterpret_cast<char*>(p.prm) + sizeof(Prm));
+    p.tab = reinterpret_cast<uint32_t*>(p.ctr + 4);
+    p.end = reinterpret_cast<char*>(p.tab) + tiletab_bytes(lay);
+    return p;
+}
+// copy the tile table (global -> shared) once per CTA; the caller synchronises before use
+__device__ __forceinline__ void stage_tiletab(const uint32_t* g, uint32_t* s_tab, int NJ, int nthreads,
+                                              int tid = threadIdx.x) {
+    const int ntiles = (int)__ldg(g + NJ);
+    for (int e = tid; e < NJ + 1 + ntiles; e += nthreads) s_tab[e] = __ldg(g + e);
 }
 
 struct FactorArgs {
@@ -116,6 +145,7 @@ struct FactorArgs {
                               // different warp for the serial diagonal block (spreads it over the SMSPs)
     const uint32_t* tiletab;  // [NJ+1] first-tile index per block column, then one packed
                               // (first row | row-pair stride << 10 | first column << 20) per tile
+    int64_t team_smem_bytes;  // shared bytes of one team (several one-warp teams may share a CTA)
     int debug_stop;       // debug: 1 = stop after the build phase (tools/occupancy_probe.py)
     long long* dbg;       // optional phase-timing buffer (tools/phase_timing.py); NULL in production
     double* out0;         // NLL: nll          DET: log det (all pivots)
@@ -204,7 +234,7 @@ struct FactorResult {  // valid in thread 0 of the team after factor_candidate()
 // broadcast.  Every slot of the panel is written (zeros above the diagonal / in dead columns,
 // y' and 1' in the two extra rows).  Rows >= n and the 8x8 diagonal corner are fixed up on
 // rarely-taken branches so the common entry costs the two exponentials and little else.
-template <int DT, bool CLAMP>
+template <int DT, bool CLAMP, bool TWOROWS>
 __device__ __forceinline__ void build_panel(const FactorArgs& A, double* Ls, const double* Xs, const double* ys,
                                             const Prm* prm, int J, int gt, int gsz) {
     const int n = A.lay.n, npad = A.lay.npad, naug = A.lay.naug, npx = A.lay.npx, d = A.d;
@@ -267,7 +297,20 @@ __device__ __forceinline__ void build_panel(const FactorArgs& A, double* Ls, con
             }
             if (!live1) v1 = 0.0;
         };
-        for (int r0 = lane; r0 < H; r0 += 32) {
+        int r0 = lane;
+        if (TWOROWS) {
+            // a lone warp has nobody to hide its latencies: two full row passes per iteration keep
+            // eight exponentials in flight (only complete 32-row passes are paired: nothing is wasted)
+            const int Pf = H >> 5;
+            for (int u = 0; u + 1 < Pf; u += 2, r0 += 64) {
+                double a0, a1, b0, b1;
+                entry2(r0, a0, a1);
+                entry2(r0 + 32, b0, b1);
+                col0[r0] = a0; col1[r0] = a1;
+                col0[r0 + 32] = b0; col1[r0 + 32] = b1;
+            }
+        }
+        for (; r0 < H; r0 += 32) {
             double v0, v1;
             entry2(r0, v0, v1);
             col0[r0] = v0;
@@ -293,12 +336,28 @@ __device__ __forceinline__ double fast_rsqrt(double x) {
 // The tile's TR rows are TR/2 row PAIRS (ia + m*rs, +1): consecutive tiles of a column group
 // take consecutive pairs, so the double2 loads/stores of consecutive lanes are consecutive
 // 16-byte words (bank-conflict free); the TC panel-row values are broadcasts.
-template <int TR, int TC>
+template <int TR, int TC, int PF>
 __device__ __forceinline__ void tile_update(double* Ls, int npad, int J, int ia, int rs, int j0) {
+    static_assert(PF == 1 || PF == 2 || PF == 4, "PF");
     const int HJ = npad - 8 * J;
     const double* pJ = Ls + blk_base(J, npad) - 8 * J;             // L(i, 8J+k) at pJ + k*HJ + i
     const int Jc = j0 >> 3, HC = npad - 8 * Jc;
     double* cb = Ls + blk_base(Jc, npad) + (j0 - 8 * Jc) * HC + (ia - 8 * Jc);   // C(ia, j0); next column + HC
+    // operands are fetched PF k-steps at a time, one group ahead of the FMAs that use them, so the
+    // shared-memory latency of group g+1 hides behind the arithmetic of group g
+    constexpr int NG = 8 / PF;
+    double2 lr[2][PF][TR / 2], lc[2][PF][TC / 2];
+    auto fetch = [&](int g, int buf) {
+#pragma unroll
+        for (int u = 0; u < PF; ++u) {
+            const double* cp = pJ + (g * PF + u) * HJ;
+#pragma unroll
+            for (int m = 0; m < TR / 2; ++m) lr[buf][u][m] = ld2(cp + ia + m * rs);
+#pragma unroll
+            for (int m = 0; m < TC / 2; ++m) lc[buf][u][m] = ld2(cp + j0 + 2 * m);
+        }
+    };
+    fetch(0, 0);
     double acc[TR][TC];
 #pragma unroll
     for (int cc = 0; cc < TC; ++cc)
@@ -308,17 +367,20 @@ __device__ __forceinline__ void tile_update(double* Ls, int npad, int J, int ia,
             acc[2 * m][cc] = v.x; acc[2 * m + 1][cc] = v.y;
         }
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const double* cp = pJ + k * HJ;
-        double lr[TR], lc[TC];
+    for (int g = 0; g < NG; ++g) {
+        if (g + 1 < NG) fetch(g + 1, (g + 1) & 1);
 #pragma unroll
-        for (int m = 0; m < TR / 2; ++m) { double2 v = ld2(cp + ia + m * rs); lr[2 * m] = v.x; lr[2 * m + 1] = v.y; }
+        for (int u = 0; u < PF; ++u)
 #pragma unroll
-        for (int m = 0; m < TC / 2; ++m) { double2 v = ld2(cp + j0 + 2 * m); lc[2 * m] = v.x; lc[2 * m + 1] = v.y; }
+            for (int m = 0; m < TR / 2; ++m)
 #pragma unroll
-        for (int r = 0; r < TR; ++r)
-#pragma unroll
-            for (int cc = 0; cc < TC; ++cc) acc[r][cc] = fma(-lr[r], lc[cc], acc[r][cc]);
+                for (int mc = 0; mc < TC / 2; ++mc) {
+                    const double2 a = lr[g & 1][u][m], b = lc[g & 1][u][mc];
+                    acc[2 * m][2 * mc] = fma(-a.x, b.x, acc[2 * m][2 * mc]);
+                    acc[2 * m][2 * mc + 1] = fma(-a.x, b.y, acc[2 * m][2 * mc + 1]);
+                    acc[2 * m + 1][2 * mc] = fma(-a.y, b.x, acc[2 * m + 1][2 * mc]);
+                    acc[2 * m + 1][2 * mc + 1] = fma(-a.y, b.y, acc[2 * m + 1][2 * mc + 1]);
+                }
     }
 #pragma unroll
     for (int cc = 0; cc < TC; ++cc)
@@ -362,15 +424,13 @@ __device__ __forceinline__ void diag_block(const FactorArgs& A, double* Ls, doub
         for (int c2 = c + 1; c2 < 8; ++c2)
 #pragma unroll
             for (int r = c2; r < 8; ++r) a[r][c2] = fma(-a[r][c], a[c2][c], a[r][c2]);
-        if (lane == c) rinv_s[c] = ri;
+        if (lane == 0) rinv_s[c] = ri;
     }
-    if (lane < 8) {                          // lane c writes column c back (rows c..7)
+    if (lane == 0) {                         // every lane holds the same block; one writes it back
 #pragma unroll
         for (int c = 0; c < 8; ++c)
-            if (lane == c) {
 #pragma unroll
-                for (int r = c; r < 8; ++r) blk[c * H + r] = a[r][c];
-            }
+            for (int r = c; r < 8; ++r) blk[c * H + r] = a[r][c];
     }
     // determinant bookkeeping off the critical chain: lane 8+c folds pivot c into its own running
     // (mantissa, exponent) pair; the 8 partial products are combined once per candidate
@@ -385,19 +445,37 @@ template <int TEAM>
 __device__ __forceinline__ void panel_trsm(double* Ls, const double* rinv_s, int npad, int J, int tid) {
     const int H = npad - 8 * J, pbase = blk_base(J, npad);
     const double* dj = Ls + pbase;            // L_JJ(c, c1) at dj[c1*H + c] (warp-wide broadcast loads)
-    for (int t = tid; t < H - 8; t += TEAM) {
+    const int nrows = H - 8;
+    // NR rows per thread at a time: their substitution chains are independent, so they interleave
+    constexpr int NR = (TEAM == 32) ? 3 : 1;
+    for (int t = tid; t < nrows; t += TEAM * NR) {
+        double x[NR][8];
         double* p = Ls + pbase + 8 + t;
-        double x[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) x[c] = p[c * H];
+        for (int q = 0; q < NR; ++q) {
+            const int tq = min(t + q * TEAM, nrows - 1);     // clamped rows recompute the last row (discarded)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) x[q][c] = Ls[pbase + 8 + tq + c * H];
+        }
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
 #pragma unroll
-            for (int c1 = 0; c1 < c; ++c1) x[c] = fma(-x[c1], dj[c1 * H + c], x[c]);
-            x[c] *= rinv_s[c];
+            for (int c1 = 0; c1 < c; ++c1) {
+                const double l = dj[c1 * H + c];
+#pragma unroll
+                for (int q = 0; q < NR; ++q) x[q][c] = fma(-x[q][c1], l, x[q][c]);
+            }
+            const double ri = rinv_s[c];
+#pragma unroll
+            for (int q = 0; q < NR; ++q) x[q][c] *= ri;
         }
 #pragma unroll
-        for (int c = 0; c < 8; ++c) p[c * H] = x[c];
+        for (int q = 0; q < NR; ++q) {
+            if (t + q * TEAM < nrows) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) p[q * TEAM + c * H] = x[q][c];
+            }
+        }
     }
 }
 
@@ -406,24 +484,23 @@ __device__ __forceinline__ void panel_trsm(double* Ls, const double* rinv_s, int
 template <int TEAM, int TR, int TC, int DT>
 __device__ __forceinline__ FactorResult factor_candidate(const FactorArgs& A, double* Ls, const double* Xs,
                                                          const double* ys, double* rinv_s, const Prm* prm, int* ctr,
-                                                         int fw) {
+                                                         const uint32_t* tab, int fw, int tid = threadIdx.x) {
     static_assert(TR == 4 || TR == 8, "TR");
     static_assert(TC == 4 || TC == 8, "TC");
     constexpr int W = TEAM / 32;
-    const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
     const int npad = A.lay.npad, NJ = A.lay.NJ;
-    const uint32_t* first = A.tiletab;               // first[Jc]: index of the first tile of block column Jc
-    const uint32_t* tiles = A.tiletab + NJ + 1;
-    const int ntiles = (int)__ldg(first + NJ);
+    const uint32_t* first = tab;                     // first[Jc]: index of the first tile of block column Jc
+    const uint32_t* tiles = tab + NJ + 1;            // (shared-memory copy of the table)
+    const int ntiles = (int)first[NJ];
 
     CCGP_T0();
     if (tid == 0) ctr[1] = 0;           // "diagonal block of panel ctr[1] is published"
     const bool clampx = prm->clamp != 0;
     for (int J = 0; J < NJ && A.debug_stop != 2; ++J) {
-        if (clampx) build_panel<DT, true>(A, Ls, Xs, ys, prm, J, tid, TEAM);
-        else build_panel<DT, false>(A, Ls, Xs, ys, prm, J, tid, TEAM);
+        if (clampx) build_panel<DT, true, (TEAM == 32)>(A, Ls, Xs, ys, prm, J, tid, TEAM);
+        else build_panel<DT, false, (TEAM == 32)>(A, Ls, Xs, ys, prm, J, tid, TEAM);
     }
     CCGP_TW(0);
     team_sync<TEAM>();
@@ -442,10 +519,10 @@ __device__ __forceinline__ FactorResult factor_candidate(const FactorArgs& A, do
 
     for (int J = 0; J + 1 < NJ; ++J) {
         // ---- U1: bring block column J+1 up to date with panel J (every thread) --------------
-        const int t1 = (int)__ldg(first + J + 1), t2 = (int)__ldg(first + J + 2);
+        const int t1 = (int)first[J + 1], t2 = (int)first[J + 2];
         for (int t = t1 + tid; t < t2; t += TEAM) {
-            const uint32_t e = __ldg(tiles + t);
-            tile_update<TR, TC>(Ls, npad, J, e & 0x3ff, (e >> 10) & 0x3ff, e >> 20);
+            const uint32_t e = tiles[t];
+            tile_update<TR, TC, (TEAM == 32 ? 4 : 2)>(Ls, npad, J, e & 0x3ff, (e >> 10) & 0x3ff, e >> 20);
         }
         if (tid == 0) *ctr = t2;
         CCGP_TW(1);
@@ -461,15 +538,27 @@ __device__ __forceinline__ FactorResult factor_candidate(const FactorArgs& A, do
             if (W > 1 && lane == 0) { __threadfence_block(); *reinterpret_cast<volatile int*>(ctr + 1) = J + 1; }
             CCGP_TW(4);
         }
-        for (;;) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(ctr, 32);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (base >= ntiles) break;
-            const int t = base + lane;
-            if (t < ntiles) {
-                const uint32_t e = __ldg(tiles + t);
-                tile_update<TR, TC>(Ls, npad, J, e & 0x3ff, (e >> 10) & 0x3ff, e >> 20);
+        if (W == 1) {
+            for (int t = t2 + lane; t < ntiles; t += 32) {
+                const uint32_t e = tiles[t];
+                tile_update<TR, TC, (TEAM == 32 ? 4 : 2)>(Ls, npad, J, e & 0x3ff, (e >> 10) & 0x3ff, e >> 20);
+            }
+        } else {
+            // chunks of 32 tiles from the shared counter; the NEXT chunk is grabbed before this one is
+            // computed so the atomic's latency hides behind the arithmetic
+            int nxt = 0;
+            if (lane == 0) nxt = atomicAdd(ctr, 32);
+            nxt = __shfl_sync(0xffffffffu, nxt, 0);
+            while (nxt < ntiles) {
+                const int base = nxt;
+                int grab = 0;
+                if (lane == 0) grab = atomicAdd(ctr, 32);
+                const int t = base + lane;
+                if (t < ntiles) {
+                    const uint32_t e = tiles[t];
+                    tile_update<TR, TC, (TEAM == 32 ? 4 : 2)>(Ls, npad, J, e & 0x3ff, (e >> 10) & 0x3ff, e >> 20);
+                }
+                nxt = __shfl_sync(0xffffffffu, grab, 0);
             }
         }
         CCGP_TW(2);
@@ -529,17 +618,17 @@ __device__ __forceinline__ void team_sum2(double& u, double& v, double* red) {
 }
 
 template <int TEAM>
-__device__ __forceinline__ void stage_design(const FactorArgs& A, int64_t dsg, double* Xs) {
+__device__ __forceinline__ void stage_design(const FactorArgs& A, int64_t dsg, double* Xs, int tid = threadIdx.x) {
     const int n = A.lay.n, npx = A.lay.npx, d = A.d;
     if (A.design_mode == DESIGN_OLD_PLUS_NEW) {
         const int n_old = A.n_old, n_new = n - n_old;
         const double* Dn = A.Dnew + dsg * (int64_t)(n_new * d);
-        for (int e = threadIdx.x; e < n * d; e += TEAM) {
+        for (int e = tid; e < n * d; e += TEAM) {
             int k = e / n, i = e - k * n;
             Xs[k * npx + i] = (i < n_old) ? A.X[k * n_old + i] : Dn[k * n_new + (i - n_old)];
         }
     } else if (A.design_mode == DESIGN_GATHER) {
-        for (int e = threadIdx.x; e < n * d; e += TEAM) {
+        for (int e = tid; e < n * d; e += TEAM) {
             int k = e / n, i = e - k * n;
             int64_t src = A.idx[dsg + A.ldi * i];
             Xs[k * npx + i] = A.X[k * A.ldpool + src];
@@ -547,20 +636,26 @@ __device__ __forceinline__ void stage_design(const FactorArgs& A, int64_t dsg, d
     }
 }
 
-template <int TEAM, int TR, int TC, int DT, int MINB>
-__global__ void __launch_bounds__(TEAM, MINB) factor_kernel(const FactorArgs A) {
-    extern __shared__ __align__(16) double smem[];
+// TPC > 1 (TEAM == 32 only): a CTA hosts TPC independent one-warp teams, each with its own slice
+// of shared memory and its own candidates.  Hardware spreads the warps of ONE CTA over the four
+// SM sub-partitions, whereas the single warps of four separate CTAs were observed to pile up on
+// one sub-partition (FP64 pipe active 27 % = one quarter) -- same residency, 4x the issue ports.
+template <int TEAM, int TR, int TC, int DT, int MINB, int TPC>
+__global__ void __launch_bounds__(TEAM * TPC, MINB) factor_kernel(const FactorArgs A) {
+    static_assert(TPC == 1 || TEAM == 32, "several teams per CTA only for one-warp teams");
+    extern __shared__ __align__(16) double smem_all[];
     const Layout& lay = A.lay;
-    double* Ls = smem;
-    double* Xs = Ls + lay.total;
-    double* ys = Xs + A.d * lay.npx;
-    double* rinv_s = ys + lay.npx;
-    double* red = rinv_s + 8;
-    Prm* prm = reinterpret_cast<Prm*>(red + 64);
-    int* ctr = reinterpret_cast<int*>(reinterpret_cast<char*>(prm) + sizeof(Prm));
-    const int tid = threadIdx.x;
+    const int team = (TPC == 1) ? 0 : (int)(threadIdx.x >> 5);
+    double* smem = smem_all + (size_t)team * (A.team_smem_bytes / 8);
+    const SmemPtrs sp = carve_smem(smem, lay, A.d);
+    double* Ls = sp.Ls; double* Xs = sp.Xs; double* ys = sp.ys; double* rinv_s = sp.rinv_s; double* red = sp.red;
+    Prm* prm = sp.prm;
+    int* ctr = sp.ctr;
+    const int tid = (TPC == 1) ? (int)threadIdx.x : (int)(threadIdx.x & 31);
+    stage_tiletab(A.tiletab, sp.tab, lay.NJ, TEAM, tid);
     const int n = lay.n, npad = lay.npad;
     const int fw = (A.num_sm > 0 ? (int)(blockIdx.x / A.num_sm) : 0) % (TEAM / 32);   // warp of the serial part
+    const int64_t w0 = (int64_t)blockIdx.x * TPC + team, wstride = (int64_t)gridDim.x * TPC;
     const int otid = fw * 32;                                                        // its lane 0 writes the outputs
 
     if (A.design_mode == DESIGN_SHARED) {
@@ -571,15 +666,15 @@ __global__ void __launch_bounds__(TEAM, MINB) factor_kernel(const FactorArgs A) 
         if (lay.naug) for (int i = tid; i < n; i += TEAM) ys[i] = A.y[i];
     }
 
-    for (int64_t w = blockIdx.x; w < A.W; w += gridDim.x) {
+    for (int64_t w = w0; w < A.W; w += wstride) {
         team_sync<TEAM>();  // previous candidate fully consumed
         const int64_t dsg = w % A.n_designs;
         const int64_t pi = (A.n_params == 1) ? 0 : w / A.n_designs;
         if (tid == 0) load_params(A, pi, prm);
-        if (A.design_mode != DESIGN_SHARED) stage_design<TEAM>(A, dsg, Xs);
+        if (A.design_mode != DESIGN_SHARED) stage_design<TEAM>(A, dsg, Xs, tid);
         team_sync<TEAM>();
 
-        FactorResult res = factor_candidate<TEAM, TR, TC, DT>(A, Ls, Xs, ys, rinv_s, prm, ctr, fw);
+        FactorResult res = factor_candidate<TEAM, TR, TC, DT>(A, Ls, Xs, ys, rinv_s, prm, ctr, sp.tab, fw, tid);
 
         if (A.out_mode == OUT_NLL) {
             double s11 = 0.0, s1y = 0.0;

@@ -45,13 +45,11 @@ __global__ void __launch_bounds__(TEAM, MINB) predict_kernel(const PredictArgs P
     extern __shared__ __align__(16) double smem[];
     const FactorArgs& A = P.F;
     const Layout& lay = A.lay;
-    double* Ls = smem;
-    double* Xs = Ls + lay.total;
-    double* ys = Xs + A.d * lay.npx;
-    double* rinv_s = ys + lay.npx;
-    double* red = rinv_s + 8;
-    Prm* prm = reinterpret_cast<Prm*>(red + 64);
-    double* extra = reinterpret_cast<double*>(reinterpret_cast<char*>(prm) + sizeof(Prm) + 16);
+    const SmemPtrs sp = carve_smem(smem, lay, A.d);
+    double* Ls = sp.Ls; double* Xs = sp.Xs; double* ys = sp.ys; double* rinv_s = sp.rinv_s; double* red = sp.red;
+    Prm* prm = sp.prm;
+    stage_tiletab(A.tiletab, sp.tab, lay.NJ, TEAM);
+    double* extra = reinterpret_cast<double*>(sp.end);
     double* rinvd = extra;
     double* z1s = rinvd + lay.npad;
     double* zrs = z1s + lay.npad;
@@ -80,7 +78,7 @@ __global__ void __launch_bounds__(TEAM, MINB) predict_kernel(const PredictArgs P
             }
         }
         __syncthreads();
-        FactorResult res = factor_candidate<TEAM, TR, TC, DT>(A, Ls, Xs, ys, rinv_s, prm, reinterpret_cast<int*>(reinterpret_cast<char*>(prm) + sizeof(Prm)), 0);
+        FactorResult res = factor_candidate<TEAM, TR, TC, DT>(A, Ls, Xs, ys, rinv_s, prm, sp.ctr, sp.tab, 0);
         if (tid == 0) red[62] = res.bad ? 1.0 : 0.0;
 
         double s11 = 0.0, s1y = 0.0;
@@ -197,13 +195,11 @@ __global__ void __launch_bounds__(TEAM, MINB) rinv_kernel(const RinvArgs P) {
     extern __shared__ __align__(16) double smem[];
     const FactorArgs& A = P.F;
     const Layout& lay = A.lay;
-    double* Ls = smem;
-    double* Xs = Ls + lay.total;
-    double* ys = Xs + A.d * lay.npx;
-    double* rinv_s = ys + lay.npx;
-    double* red = rinv_s + 8;
-    Prm* prm = reinterpret_cast<Prm*>(red + 64);
-    double* extra = reinterpret_cast<double*>(reinterpret_cast<char*>(prm) + sizeof(Prm) + 16);
+    const SmemPtrs sp = carve_smem(smem, lay, A.d);
+    double* Ls = sp.Ls; double* Xs = sp.Xs; double* ys = sp.ys; double* rinv_s = sp.rinv_s; double* red = sp.red;
+    Prm* prm = sp.prm;
+    stage_tiletab(A.tiletab, sp.tab, lay.NJ, TEAM);
+    double* extra = reinterpret_cast<double*>(sp.end);
     double* rinvd = extra;
     double* vbuf = rinvd + lay.npad;  // [warp][npad]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -219,7 +215,7 @@ __global__ void __launch_bounds__(TEAM, MINB) rinv_kernel(const RinvArgs P) {
         __syncthreads();
         if (tid == 0) load_params(A, s, prm);
         __syncthreads();
-        FactorResult res = factor_candidate<TEAM, TR, TC, 0>(A, Ls, Xs, ys, rinv_s, prm, reinterpret_cast<int*>(reinterpret_cast<char*>(prm) + sizeof(Prm)), 0);
+        FactorResult res = factor_candidate<TEAM, TR, TC, 0>(A, Ls, Xs, ys, rinv_s, prm, sp.ctr, sp.tab, 0);
         if (tid == 0) red[62] = res.bad ? 1.0 : 0.0;
         double s11 = 0.0, s1y = 0.0;
         for (int k = tid; k < n; k += TEAM) {

@@ -14,7 +14,8 @@ import ccgp_b200  # noqa: E402
 from ccgp_b200 import workloads, GAUSS_ISO, GAUSS_ANISO_LAMBDA, LOGSCALE, MEAN_ZERO_PLUS_TAU2  # noqa: E402
 
 VARIANTS = [(32, 4, 4), (32, 8, 4), (64, 4, 4), (64, 8, 4), (64, 4, 8), (128, 4, 4), (128, 8, 4), (128, 4, 8),
-            (256, 4, 4), (256, 4, 4), (32, 8, 4), (32, 4, 4), (32, 8, 8), (96, 4, 4), (64, 8, 4), (128, 4, 4)]
+            (256, 4, 4), (256, 4, 4), (32, 8, 4), (32, 4, 4), (32, 8, 8), (96, 4, 4), (64, 8, 4), (128, 4, 4),
+            (32, 4, 4), (32, 8, 4), (32, 4, 4), (32, 4, 4), (32, 4, 8)]
 
 
 def main():
