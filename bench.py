@@ -315,7 +315,9 @@ def run_ours(args, rank, world, local_rank):
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             try:
-                traffic = json.load(open(tpath)).get("nll_kernel_dram_bytes_per_launch")
+                tj = json.load(open(tpath))
+                # ncu dram__bytes_read+write of one captured launch, scaled to this launch's candidate count
+                traffic = tj["nll_kernel_dram_bytes_per_launch"] / tj["candidates_per_launch"] * B
             except Exception:
                 traffic = None
         line = {

@@ -110,11 +110,14 @@ static int get_tiletab(ccgp_ctx* ctx, const Layout& l, int TR, int TC, const uin
         first[Jc] = (uint32_t)tiles.size();
         const int H = l.npad - 8 * Jc;      // multiple of 8, so H/TR tiles of TR/2 pairs each
         const int Nt = H / TR;
-        for (int cg = 0; cg < 8 / TC; ++cg) {
-            const int j0 = 8 * Jc + TC * cg;
-            for (int t = 0; t < Nt; ++t)
-                tiles.push_back((uint32_t)(8 * Jc + 2 * t) | ((uint32_t)(2 * Nt) << 10) | ((uint32_t)j0 << 20));
-        }
+        // the tiles whose first pair lies in the 8 diagonal-block rows (t < 4) lead the block column
+        const int lead = std::min(Nt, 4);
+        for (int pass = 0; pass < 2; ++pass)
+            for (int cg = 0; cg < 8 / TC; ++cg) {
+                const int j0 = 8 * Jc + TC * cg;
+                for (int t = (pass == 0 ? 0 : lead); t < (pass == 0 ? lead : Nt); ++t)
+                    tiles.push_back((uint32_t)(8 * Jc + 2 * t) | ((uint32_t)(2 * Nt) << 10) | ((uint32_t)j0 << 20));
+            }
     }
     first[l.NJ] = (uint32_t)tiles.size();
     std::vector<uint32_t> h(first);

@@ -82,12 +82,12 @@ inline Layout make_layout(int n, int naug) {
     return l;
 }
 
-// shared bytes: L | Xs[d*npx] | ys[npx] | rinv[8] | red[64] | Prm | ints[4] | tile table
+// shared bytes: L | Xs[d*npx] | ys[npx] | rinv[8] | red[64] | Prm | ints[8] | tile table
 // (the table has NJ+1 + total/(TR*TC) <= NJ+1 + total/16 entries)
 __host__ __device__ __forceinline__ size_t tiletab_bytes(const Layout& l) { return ((size_t)l.NJ + 1 + l.total / 16 + 3) / 4 * 16; }
 inline size_t smem_bytes(const Layout& l, int d) {
     size_t dbl = (size_t)l.total + (size_t)d * l.npx + l.npx + 8 + 64;
-    return dbl * 8 + sizeof(Prm) + 16 + tiletab_bytes(l);
+    return dbl * 8 + sizeof(Prm) + 32 + tiletab_bytes(l);
 }
 
 struct SmemPtrs {
@@ -106,7 +106,7 @@ __device__ __forceinline__ SmemPtrs carve_smem(double* smem, const Layout& lay, 
     p.red = p.rinv_s + 8;
     p.prm = reinterpret_cast<Prm*>(p.red + 64);
     p.ctr = reinterpret_cast<int*>(reinterpret_cast<char*>(p.prm) + sizeof(Prm));
-    p.tab = reinterpret_cast<uint32_t*>(p.ctr + 4);
+    p.tab = reinterpret_cast<uint32_t*>(p.ctr + 8);
     p.end = reinterpret_cast<char*>(p.tab) + tiletab_bytes(lay);
     return p;
 }
@@ -496,7 +496,10 @@ __device__ __forceinline__ FactorResult factor_candidate(const FactorArgs& A, do
     const int ntiles = (int)first[NJ];
 
     CCGP_T0();
-    if (tid == 0) ctr[1] = 0;           // "diagonal block of panel ctr[1] is published"
+    if (tid == 0) {
+        ctr[2] = 0;                                           // "diagonal block of panel ctr[2] is published"
+        if (NJ > 1) { ctr[0] = (int)tab[1] + min((npad - 8) / TR, 4) * (8 / TC); ctr[3] = 0; }
+    }
     const bool clampx = prm->clamp != 0;
     for (int J = 0; J < NJ && A.debug_stop != 2; ++J) {
         if (clampx) build_panel<DT, true, (TEAM == 32)>(A, Ls, Xs, ys, prm, J, tid, TEAM);
@@ -517,57 +520,70 @@ __device__ __forceinline__ FactorResult factor_candidate(const FactorArgs& A, do
     team_sync<TEAM>();
     CCGP_TB(3);
 
+    // ---- one team barrier per step ----------------------------------------------------------
+    // step J applies factored panel J to the trailing matrix.  The serial warp first updates the
+    // tiles that hold the diagonal block of panel J+1 (they lead block column J+1 in the table),
+    // factors that block and publishes it (flag); meanwhile the other warps take the remaining
+    // tiles in chunks from a shared counter (the serial warp joins when done).  Panel J+1's rows
+    // are solved as soon as the flag is up and every tile of block column J+1 is finished
+    // (completion counter).  Counters alternate between two slots so the next step's can be armed
+    // while this step still uses its own.
+    constexpr int PFK = (TEAM == 32 ? 4 : 2);
+    constexpr int CGN = 8 / TC;
+    volatile int* flag = reinterpret_cast<volatile int*>(ctr + 2);
     for (int J = 0; J + 1 < NJ; ++J) {
-        // ---- U1: bring block column J+1 up to date with panel J (every thread) --------------
         const int t1 = (int)first[J + 1], t2 = (int)first[J + 2];
-        for (int t = t1 + tid; t < t2; t += TEAM) {
-            const uint32_t e = tiles[t];
-            tile_update<TR, TC, (TEAM == 32 ? 4 : 2)>(Ls, npad, J, e & 0x3ff, (e >> 10) & 0x3ff, e >> 20);
+        const int nd = min((npad - 8 * (J + 1)) / TR, 4) * CGN;    // leading tiles = diagonal block of panel J+1
+        const int need = t2 - t1 - nd;
+        int* cnt = ctr + (J & 1);
+        int* dn = ctr + 3 + (J & 1);
+        if (W > 1 && tid == 0 && J + 2 < NJ) {                     // arm the next step's slots
+            const int ndn = min((npad - 8 * (J + 2)) / TR, 4) * CGN;
+            ctr[(J + 1) & 1] = t2 + ndn;
+            ctr[3 + ((J + 1) & 1)] = 0;
         }
-        if (tid == 0) *ctr = t2;
-        CCGP_TW(1);
-        team_sync<TEAM>();
-        CCGP_TB(1);
-        // ---- lookahead: warp 0 factors the diagonal block of panel J+1 while the others apply
-        //      panel J to the rest of the trailing matrix; warp 0 joins when it is done.  The rows
-        //      of panel J+1 are solved in the same phase as soon as the diagonal block is published
-        //      (flag in shared memory), so a step costs two team barriers.
         if (warp == fw) {
+            if (lane < nd) {
+                const uint32_t e = tiles[t1 + lane];
+                tile_update<TR, TC, PFK>(Ls, npad, J, e & 0x3ff, (e >> 10) & 0x3ff, e >> 20);
+            }
+            __syncwarp();
             diag_block(A, Ls, rinv_s, J + 1, lane, res);
             __syncwarp();
-            if (W > 1 && lane == 0) { __threadfence_block(); *reinterpret_cast<volatile int*>(ctr + 1) = J + 1; }
+            if (W > 1 && lane == 0) { __threadfence_block(); *flag = J + 1; }
             CCGP_TW(4);
         }
         if (W == 1) {
-            for (int t = t2 + lane; t < ntiles; t += 32) {
+            for (int t = t1 + nd + lane; t < ntiles; t += 32) {
                 const uint32_t e = tiles[t];
-                tile_update<TR, TC, (TEAM == 32 ? 4 : 2)>(Ls, npad, J, e & 0x3ff, (e >> 10) & 0x3ff, e >> 20);
+                tile_update<TR, TC, PFK>(Ls, npad, J, e & 0x3ff, (e >> 10) & 0x3ff, e >> 20);
             }
+            __syncwarp();
         } else {
-            // chunks of 32 tiles from the shared counter; the NEXT chunk is grabbed before this one is
-            // computed so the atomic's latency hides behind the arithmetic
+            // the NEXT chunk is grabbed before this one is computed: the atomic's latency hides
             int nxt = 0;
-            if (lane == 0) nxt = atomicAdd(ctr, 32);
+            if (lane == 0) nxt = atomicAdd(cnt, 32);
             nxt = __shfl_sync(0xffffffffu, nxt, 0);
             while (nxt < ntiles) {
                 const int base = nxt;
                 int grab = 0;
-                if (lane == 0) grab = atomicAdd(ctr, 32);
+                if (lane == 0) grab = atomicAdd(cnt, 32);
                 const int t = base + lane;
                 if (t < ntiles) {
                     const uint32_t e = tiles[t];
-                    tile_update<TR, TC, (TEAM == 32 ? 4 : 2)>(Ls, npad, J, e & 0x3ff, (e >> 10) & 0x3ff, e >> 20);
+                    tile_update<TR, TC, PFK>(Ls, npad, J, e & 0x3ff, (e >> 10) & 0x3ff, e >> 20);
                 }
+                const int incol = min(base + 32, t2) - base;       // tiles of block column J+1 in this chunk
+                __syncwarp();
+                if (incol > 0 && lane == 0) { __threadfence_block(); atomicAdd(dn, incol); }
                 nxt = __shfl_sync(0xffffffffu, grab, 0);
             }
-        }
-        CCGP_TW(2);
-        if (W > 1 && warp != fw) {
-            while (*reinterpret_cast<volatile int*>(ctr + 1) < J + 1) { }
+            CCGP_TW(2);
+            while (*flag < J + 1 || *reinterpret_cast<volatile int*>(dn) < need) { }
             __threadfence_block();
+            __syncwarp();
+            CCGP_TB(2);
         }
-        __syncwarp();
-        CCGP_TB(2);
         // ---- rows of panel J+1 below its diagonal block ---------------------------------------
         panel_trsm<TEAM>(Ls, rinv_s, npad, J + 1, tid);
         CCGP_TW(3);
