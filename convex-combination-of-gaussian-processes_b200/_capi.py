@@ -10,7 +10,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libccgp.so")
 
 # every symbol include/ccgp.h declares (tests check that the .so exports them all)
 SYMBOLS = [
-    "ccgp_num_params", "ccgp_create", "ccgp_destroy", "ccgp_last_error", "ccgp_sync", "ccgp_set_stream", "ccgp_use_own_stream", "ccgp_device",
+    "ccgp_num_params", "ccgp_create", "ccgp_destroy", "ccgp_last_error", "ccgp_sync", "ccgp_set_matern_nu", "ccgp_set_stream", "ccgp_use_own_stream", "ccgp_device",
     "ccgp_launch_count", "ccgp_last_nll_config", "ccgp_measure_fp64_peak", "ccgp_set_design",
     "ccgp_nll_batch", "ccgp_nll_batch_dev", "ccgp_argmin_dev", "ccgp_nll_argmin", "ccgp_rinv_batch",
     "ccgp_predict", "ccgp_predict_dev", "ccgp_me_schur_batch", "ccgp_me_schur_batch_dev", "ccgp_me_argmin",
@@ -41,6 +41,7 @@ def load():
     lib.ccgp_last_error.argtypes = [vp]
     lib.ccgp_last_error.restype = C.c_char_p
     lib.ccgp_sync.argtypes = [vp]
+    lib.ccgp_set_matern_nu.argtypes = [vp, f64]
     lib.ccgp_set_stream.argtypes = [vp, vp]
     lib.ccgp_use_own_stream.argtypes = [vp]
     lib.ccgp_device.argtypes = [vp]

@@ -27,6 +27,8 @@ struct ccgp_ctx {
     double* d_X = nullptr;
     double* d_y = nullptr;
     double span2[MAXD] = {0};   // squared coordinate ranges of the shared design
+    int twonu = 10;             // Matern smoothness of the 1-D families, 2*nu (reference default nu = 5)
+    double mnorm = 1.0 / 384.0; // 1 / (Gamma(nu) 2^(nu-1))
     std::map<std::vector<int>, uint32_t*> tiletabs;   // (n, naug, TR, TC) -> tile table
     void* ws = nullptr;       // device workspace for the host-pointer entry points
     size_t ws_bytes = 0;
@@ -175,7 +177,8 @@ static int launch_factor(ccgp_ctx* ctx, FactorArgs& A) {
     if (grid * var.tpc > A.W) grid = (A.W + var.tpc - 1) / var.tpc;
     if (grid < 1) return 0;
     A.dbg = ctx->dbg;
-    A.num_sm = env_int("CCGP_NO_ROTATE", 0) ? 0 : ctx->num_sm;
+    A.num_sm = env_int("CCGP_ROTATE", 0) ? ctx->num_sm : 0;    // rotation measured no better than warp 0 (profiles/)
+    if (env_int("CCGP_FW", -1) >= 0) A.num_sm = -(env_int("CCGP_FW", 0) + 1);
     A.debug_stop = env_int("CCGP_DEBUG_STOP", 0);
     RC(get_tiletab(ctx, l, var.tr, var.tc, &A.tiletab));
     fn<<<(unsigned)grid, var.team * var.tpc, smem, ctx->stream>>>(A);
@@ -188,6 +191,7 @@ static int launch_factor(ccgp_ctx* ctx, FactorArgs& A) {
 // ------------------------------------------------------------------ context
 extern "C" int ccgp_num_params(int family, int d) {
     if (family == CCGP_GAUSS_ISO || family == CCGP_GAUSS_ISO_RAW2) return 3;
+    if (family == CCGP_MATERN1D || family == CCGP_MATERN_SPLINE1D) return 3;
     if (family == CCGP_GAUSS_ANISO_LAMBDA) return d + 2;
     return -1;
 }
@@ -261,6 +265,15 @@ extern "C" int ccgp_use_own_stream(ccgp_ctx* ctx) {
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->stream = ctx->own_stream;
+    return CCGP_OK;
+}
+
+extern "C" int ccgp_set_matern_nu(ccgp_ctx* ctx, double nu) {
+    if (!ctx) return CCGP_ERR_ARG;
+    const double t2 = 2.0 * nu;
+    ARG(nu > 0 && nu <= 50 && t2 == (double)(int)t2);   // integer or half-integer smoothness
+    ctx->twonu = (int)t2;
+    ctx->mnorm = 1.0 / (tgamma(nu) * pow(2.0, nu - 1.0));
     return CCGP_OK;
 }
 
@@ -351,7 +364,8 @@ extern "C" int ccgp_set_design(ccgp_ctx* ctx, const double* X, int n, int d, con
 static int check_nll_args(ccgp_ctx* ctx, int family, int scale, const void* cand, int64_t B, int64_t ldc,
                           double sigma2, int mean_mode) {
     ARG(ctx->n > 0);
-    ARG(family >= 0 && family <= 2);
+    ARG(family >= 0 && family <= 4);
+    ARG(family < CCGP_MATERN1D || ctx->d == 1);     // the Matern / spline families are the 1-D scripts'
     ARG(scale == 0 || scale == 1);
     ARG(mean_mode == 0 || mean_mode == 1);
     ARG(B >= 0 && ldc >= B);
@@ -371,6 +385,10 @@ extern "C" int ccgp_nll_batch_dev(ccgp_ctx* ctx, int family, int scale, const do
     CK(cudaSetDevice(ctx->device));
     Layout l = make_layout(ctx->n, 2);
     if (smem_bytes(l, ctx->d) > (size_t)ctx->max_smem_optin || env_int("CCGP_FORCE_BIG", 0)) {
+        if (family >= CCGP_MATERN1D) {
+            snprintf(ctx->err, sizeof(ctx->err), "1-D Matern/spline families are limited to the shared-memory path (n <= ~220)");
+            return CCGP_ERR_UNSUPPORTED;
+        }
         return bigchol_nll_batch(ctx->big, ctx->stream, ctx->num_sm, ctx->d_X, ctx->d_y, ctx->n, ctx->d, family, scale,
                                  d_cand, B, ldc, sigma2, mean_mode, tau, d_nll, d_beta, d_status, &ctx->launches,
                                  ctx->err, sizeof(ctx->err));
@@ -379,7 +397,7 @@ extern "C" int ccgp_nll_batch_dev(ccgp_ctx* ctx, int family, int scale, const do
     memset(&A, 0, sizeof(A));
     A.lay = l;
     A.d = ctx->d;
-    A.design_mode = DESIGN_SHARED; memcpy(A.span2, ctx->span2, sizeof(A.span2));
+    A.design_mode = DESIGN_SHARED; memcpy(A.span2, ctx->span2, sizeof(A.span2)); A.twonu = ctx->twonu; A.mnorm = ctx->mnorm;
     A.X = ctx->d_X;
     A.y = ctx->d_y;
     A.n_designs = 1;
@@ -565,7 +583,7 @@ extern "C" int ccgp_rinv_batch(ccgp_ctx* ctx, int family, int scale, const doubl
     RinvArgs P;
     memset(&P, 0, sizeof(P));
     FactorArgs& A = P.F;
-    A.lay = l; A.d = ctx->d; A.design_mode = DESIGN_SHARED; memcpy(A.span2, ctx->span2, sizeof(A.span2)); A.X = ctx->d_X; A.y = ctx->d_y; A.n_designs = 1;
+    A.lay = l; A.d = ctx->d; A.design_mode = DESIGN_SHARED; memcpy(A.span2, ctx->span2, sizeof(A.span2)); A.twonu = ctx->twonu; A.mnorm = ctx->mnorm; A.X = ctx->d_X; A.y = ctx->d_y; A.n_designs = 1;
     A.cand = d_cand; A.ldc = B; A.n_params = B; A.family = family; A.logscale = scale; A.sigma2 = 1.0; A.W = B;
     A.out_mode = OUT_NLL;
     P.out_rinv = d_rinv; P.out_beta = d_beta; P.status = d_status;
@@ -611,21 +629,24 @@ extern "C" int ccgp_predict_dev(ccgp_ctx* ctx, int family, const double* d_pars,
                                 int64_t T, double sigma2, double* d_mean, double* d_var, int32_t* d_status) {
     if (!ctx) return CCGP_ERR_ARG;
     ARG(ctx->n > 0);
-    ARG(family >= 0 && family <= 2);
+    ARG(family >= 0 && family <= 4);
+    ARG(family < CCGP_MATERN1D || ctx->d == 1);
     ARG(S >= 0 && T >= 0 && ldp >= S);
     ARG(sigma2 > 0);
     if (S == 0 || T == 0) return CCGP_OK;
     ARG(d_pars && d_Xnew && d_mean && d_var);
-    ARG(d_pars_vec == nullptr || (vec_family >= 0 && vec_family <= 2 && ldpv >= S));
+    ARG(d_pars_vec == nullptr || (vec_family >= 0 && vec_family <= 4 && ldpv >= S));
     CK(cudaSetDevice(ctx->device));
     PredictArgs P;
     memset(&P, 0, sizeof(P));
     FactorArgs& A = P.F;
     A.lay = make_layout(ctx->n, 2);
-    A.d = ctx->d; A.design_mode = DESIGN_SHARED; memcpy(A.span2, ctx->span2, sizeof(A.span2)); A.X = ctx->d_X; A.y = ctx->d_y; A.n_designs = 1;
+    A.d = ctx->d; A.design_mode = DESIGN_SHARED; memcpy(A.span2, ctx->span2, sizeof(A.span2)); A.twonu = ctx->twonu; A.mnorm = ctx->mnorm; A.X = ctx->d_X; A.y = ctx->d_y; A.n_designs = 1;
     A.cand = d_pars; A.ldc = ldp; A.n_params = S; A.family = family; A.logscale = 0; A.sigma2 = sigma2; A.W = S;
     A.out_mode = OUT_NLL;
     P.Xnew = d_Xnew; P.T = T; P.candv = d_pars_vec; P.ldcv = ldpv; P.vec_family = vec_family;
+    // quirk Q3: corr.vec.combined ([D2]:472-480) returns before dividing by p^2 + (1-p)^2
+    P.vec_unnormalised = (family == CCGP_MATERN_SPLINE1D && !env_int("CCGP_NO_Q3", 0)) ? 1 : 0;
     P.out_mean = d_mean; P.out_var = d_var; P.status = d_status;
     const int n = ctx->n;
     if (n <= 32) return launch_predict<64, 4, 4, 1, 8>(ctx, P);
@@ -644,7 +665,7 @@ extern "C" int ccgp_predict(ccgp_ctx* ctx, int family, const double* pars, int64
     ARG(S >= 0 && T >= 0 && ldp >= S);
     if (S == 0 || T == 0) return CCGP_OK;
     ARG(pars && Xnew && out_mean && out_var);
-    ARG(family >= 0 && family <= 2);
+    ARG(family >= 0 && family <= 4);
     CK(cudaSetDevice(ctx->device));
     const int d = ctx->d, k = ccgp_num_params(family, d);
     const int kv = pars_vec ? ccgp_num_params(vec_family, d) : 0;
@@ -822,12 +843,17 @@ __global__ void __launch_bounds__(256) mixed_corr_kernel(FactorArgs F, const dou
     const int d = F.d;
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < (int64_t)na * nb; e += (int64_t)gridDim.x * blockDim.x) {
         int i = (int)(e % na), j = (int)(e / na);
-        double s1 = 0.0;
-        for (int k = 0; k < d; ++k) {
-            double df = Am[i + (int64_t)na * k] - Bm[j + (int64_t)nb * k];
-            s1 = fma(prm.wts[k] * df, df, s1);
+        double v;
+        if (prm.kind != 0) {
+            v = corr1d(&prm, fabs(Am[i] - Bm[j]));
+        } else {
+            double s1 = 0.0;
+            for (int k = 0; k < d; ++k) {
+                double df = Am[i + (int64_t)na * k] - Bm[j + (int64_t)nb * k];
+                s1 = fma(prm.wts[k] * df, df, s1);
+            }
+            v = fma(prm.b, dexp_neg(prm.rho * s1), prm.a * dexp_neg(s1));
         }
-        double v = fma(prm.b, dexp_neg(prm.rho * s1), prm.a * dexp_neg(s1));
         if (same && i == j) v = 1.0;
         out[e] = v;
     }
@@ -836,7 +862,8 @@ __global__ void __launch_bounds__(256) mixed_corr_kernel(FactorArgs F, const dou
 extern "C" int ccgp_mixed_corr(ccgp_ctx* ctx, int family, const double* params, const double* A, int na,
                                const double* B, int nb, int d, double* out) {
     if (!ctx) return CCGP_ERR_ARG;
-    ARG(family >= 0 && family <= 2 && params && A && out && na >= 1 && d >= 1 && d <= MAXD);
+    ARG(family >= 0 && family <= 4 && params && A && out && na >= 1 && d >= 1 && d <= MAXD);
+    ARG(family < CCGP_MATERN1D || d == 1);
     ARG(B == nullptr || nb >= 1);
     CK(cudaSetDevice(ctx->device));
     const int same = (B == nullptr);
@@ -853,6 +880,7 @@ extern "C" int ccgp_mixed_corr(ccgp_ctx* ctx, int family, const double* params, 
     if (!same) CK(cudaMemcpyAsync(d_B, B, (size_t)nb * d * 8, cudaMemcpyHostToDevice, ctx->stream));
     FactorArgs F;
     memset(&F, 0, sizeof(F));
+    F.twonu = ctx->twonu; F.mnorm = ctx->mnorm;
     F.force_clamp = 1; F.d = d; F.cand = d_par; F.ldc = 1; F.n_params = 1; F.family = family; F.logscale = 0; F.sigma2 = 1.0;
     int64_t tot = (int64_t)na * nb;
     int grid = (int)std::min<int64_t>((tot + 255) / 256, (int64_t)ctx->num_sm * 8);

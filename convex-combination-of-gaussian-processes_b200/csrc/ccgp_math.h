@@ -90,3 +90,86 @@ CCGP_HD double dexp_neg(double s) {
     if (s > 690.0) return 0.0;
     return ccgp_scale2(e, k);
 }
+
+
+// ------------------------------------------------------------------------------------------
+// 1-D component kernels of the reference's one-dimensional scripts:
+//   Matern.corr.func  ([D1]:348-351 = "1D Combined GP Public.R"): t^nu K_nu(t) / (Gamma(nu) 2^(nu-1)),
+//                     t = 2 sqrt(nu) |h| / theta, 1 at h = 0
+//   spline.corr.func  ([D2]:346-357 = "1D Combined GP Two Families Public.R"): cubic spline, support theta
+// K_nu for integer nu comes from K0, K1 and the upward recurrence K_{m+1} = K_{m-1} + (2m/t) K_m
+// (all terms positive: stable); half-integer nu starts from K_{1/2} = sqrt(pi/2t) e^-t.
+// K0/K1: exact power series for t <= 2, Chebyshev expansion of sqrt(2t/pi) e^t K(t) in 4/t - 1
+// beyond (tables from tools/gen_bessel_coeffs.py, 50-digit mpmath).
+#if defined(__CUDA_ARCH__)
+#define CCGP_CONST __device__ const
+#else
+#define CCGP_CONST static const
+#endif
+// I0 series: sum a0[k] z^k, z = t^2/4
+CCGP_CONST double BES_I0[16] = {1.0, 1.0, 0.25, 0.027777777777777776, 0.001736111111111111, 6.944444444444444e-05, 1.9290123456790124e-06, 3.936759889140842e-08, 6.151187326782565e-10, 7.594058428126624e-12, 7.594058428126623e-14, 6.276081345559193e-16, 4.358389823304995e-18, 2.5789288895295828e-20, 1.3157800456783586e-22, 5.8479113141260385e-25};
+CCGP_CONST double BES_K0P[16] = {-0.5772156649015329, 0.42278433509846713, 0.23069608377461678, 0.0348921574564389, 0.0026147876188052093, 0.00011848039364109726, 3.6126241031992037e-06, 7.935096521304209e-08, 1.3167486730385647e-09, 1.709994072705808e-11, 1.785934656987074e-13, 1.5330343403208473e-15, 1.1009270959725744e-17, 6.712740659979047e-20, 3.518851972639805e-22, 1.6029202854896424e-24};
+CCGP_CONST double BES_I1[16] = {1.0, 0.5, 0.08333333333333333, 0.006944444444444444, 0.00034722222222222224, 1.1574074074074073e-05, 2.755731922398589e-07, 4.920949861426052e-09, 6.834652585313961e-11, 7.594058428126623e-13, 6.903689480115112e-15, 5.230067787965994e-17, 3.352607556388458e-19, 1.842092063949702e-21, 8.771866971189057e-24, 3.654944571328774e-26};
+CCGP_CONST double BES_K1P[16] = {-0.15443132980306573, 0.6727843350984671, 0.18157516696085563, 0.019182189839330562, 0.001115359491966528, 4.142247689271143e-05, 1.071545914091181e-06, 2.045286003593878e-08, 3.002048746589188e-10, 3.495928729692882e-12, 3.309914735250272e-14, 2.5986411321011286e-16, 1.7195232826992565e-18, 9.721207518823618e-21, 4.750281743327667e-23, 2.0264937604328578e-25};
+CCGP_CONST double BES_K0A[26] = {1.9470801528600736, -0.02509195450338081, 0.0012525861146772193, -0.00010252457224451742, 1.1130340992367562e-05, -1.4615294507429678e-06, 2.2075978855319634e-07, -3.718532935142939e-08, 6.841089366293377e-09, -1.3544365764715988e-09, 2.8543500586874657e-10, -6.349157810923372e-11, 1.480833144458278e-11, -3.602127949377824e-12, 9.09860149387498e-13, -2.3777733246760547e-13, 6.409319528042818e-14, -1.7772984923934982e-14, 5.05864913473057e-15, -1.4749641154455083e-15, 4.3979843802055255e-16, -1.3390347046986472e-16, 4.157291155115988e-17, -1.3145791186184579e-17, 4.229134271580504e-18, -1.3828705421726237e-18};  // Chebyshev, c[0] is halved at evaluation
+CCGP_CONST double BES_K1A[26] = {2.170745633103452, 0.0829191449155865, -0.0022802079498951454, 0.00015575944821741804, -1.5448624702449026e-05, 1.9200971856838045e-06, -2.7941602977436566e-07, 4.580722385967015e-08, -8.254724141098338e-09, 1.6077770889213073e-09, -3.343419366765729e-10, 7.35515136480485e-11, -1.6994684532881865e-11, 4.100839143561442e-12, -1.0286119996309399e-12, 2.671652354631771e-13, -7.162374471604971e-14, 1.9764832698093292e-14, -5.6010196328357906e-15, 1.6266497804027024e-15, -4.832824501299199e-16, 1.4665864849973659e-16, -4.539534566633093e-17, 1.4314456324007267e-17, -4.593217542733376e-18, 1.4983196424996574e-18};  // Chebyshev, c[0] is halved at evaluation
+
+CCGP_HD void ccgp_bessel_k01(double t, double* k0, double* k1) {
+    if (t <= 2.0) {
+        const double z = 0.25 * t * t;
+        double i0 = 0.0, p0 = 0.0, i1 = 0.0, p1 = 0.0;
+        for (int k = 15; k >= 0; --k) {
+            i0 = fma(i0, z, BES_I0[k]);
+            p0 = fma(p0, z, BES_K0P[k]);
+            i1 = fma(i1, z, BES_I1[k]);
+            p1 = fma(p1, z, BES_K1P[k]);
+        }
+        const double lg = log(0.5 * t);
+        *k0 = fma(-lg, i0, p0);
+        *k1 = 1.0 / t + 0.5 * t * (lg * i1 - 0.5 * p1);
+    } else {
+        const double s = 4.0 / t - 1.0, s2 = 2.0 * s;
+        double b0 = 0.0, b1 = 0.0, c0 = 0.0, c1 = 0.0;
+        for (int k = 25; k >= 1; --k) {
+            const double tb = fma(s2, b0, BES_K0A[k]) - b1; b1 = b0; b0 = tb;
+            const double tc = fma(s2, c0, BES_K1A[k]) - c1; c1 = c0; c0 = tc;
+        }
+        const double f0 = fma(s, b0, 0.5 * BES_K0A[0]) - b1;
+        const double f1 = fma(s, c0, 0.5 * BES_K1A[0]) - c1;
+        const double sc = sqrt(1.5707963267948966 / t) * exp(-t);
+        *k0 = sc * f0;
+        *k1 = sc * f1;
+    }
+}
+
+// Matern correlation at scaled distance t = 2 sqrt(nu) |h| / theta; twonu = 2 nu (integer),
+// norm = 1 / (Gamma(nu) 2^(nu-1))
+CCGP_HD double ccgp_matern(double t, int twonu, double norm) {
+    if (!(t > 0.0)) return 1.0;
+    if (t > 700.0) return 0.0;
+    double km, kc, mu;          // K_{mu-1}, K_mu
+    if (twonu & 1) {
+        const double sc = sqrt(1.5707963267948966 / t) * exp(-t);
+        km = sc; kc = sc * (1.0 + 1.0 / t); mu = 1.5;          // K_{1/2}, K_{3/2}
+        if (twonu == 1) kc = km;
+    } else {
+        ccgp_bessel_k01(t, &km, &kc); mu = 1.0;                 // K_0, K_1
+        if (twonu == 0) kc = km;
+    }
+    const double two_over_t = 2.0 / t;
+    for (int m = (twonu & 1) ? 3 : 2; m < twonu; m += 2) {      // raise the order to nu
+        const double kn = fma(mu * two_over_t, kc, km);
+        km = kc; kc = kn; mu += 1.0;
+    }
+    double pw = 1.0;
+    for (int m = 0; m < (twonu >> 1); ++m) pw *= t;
+    if (twonu & 1) pw *= sqrt(t);
+    return pw * kc * norm;
+}
+
+// cubic-spline correlation at u = |h| / theta
+CCGP_HD double ccgp_spline(double u) {
+    if (u <= 0.5) return fma(6.0 * u * u, u - 1.0, 1.0);
+    if (u <= 1.0) { const double v = 1.0 - u; return 2.0 * v * v * v; }
+    return 0.0;
+}

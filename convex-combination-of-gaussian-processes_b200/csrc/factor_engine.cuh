@@ -46,7 +46,7 @@ constexpr double PIVOT_MIN = 64 * 2.220446049250313e-16;
 constexpr double LOG2PI = 1.8378770664093454835606594728112;
 constexpr double LN2 = 0.69314718055994530941723212145818;
 
-enum { FAM_ISO = 0, FAM_ANISO = 1, FAM_ISO_RAW2 = 2 };
+enum { FAM_ISO = 0, FAM_ANISO = 1, FAM_ISO_RAW2 = 2, FAM_MATERN1D = 3, FAM_MATERN_SPLINE1D = 4 };
 enum { OUT_NLL = 0, OUT_DET = 1 };
 enum { DESIGN_SHARED = 0, DESIGN_OLD_PLUS_NEW = 1, DESIGN_GATHER = 2 };
 
@@ -57,8 +57,20 @@ struct Prm {  // per-candidate parameters, one copy in shared memory
     double c;          // w * sigma2
     double p;
     int clamp;         // 1: exponents may exceed 1e8 -> use the argument-clamping exp
+    int kind;          // 0 Gaussian components; 1 Matern + Matern; 2 Matern + cubic spline (1-D scripts)
+    double c1, c2;     // 1-D kinds: distance scales (2 sqrt(nu)/theta1; 2 sqrt(nu)/theta2 or 1/theta2)
+    double mnorm;      // 1 / (Gamma(nu) 2^(nu-1))
+    double w;          // p^2 + (1-p)^2
+    int twonu;         // 2 nu
     int pad_;
 };
+
+// mixed correlation of two 1-D sites at distance h for the Matern / spline kinds
+__device__ __forceinline__ double corr1d(const Prm* prm, double h) {
+    const double m1 = ccgp_matern(prm->c1 * h, prm->twonu, prm->mnorm);
+    const double m2 = (prm->kind == 1) ? ccgp_matern(prm->c2 * h, prm->twonu, prm->mnorm) : ccgp_spline(prm->c2 * h);
+    return fma(prm->b, m2, prm->a * m1);
+}
 
 struct Layout {
     int n;      // design points
@@ -139,6 +151,8 @@ struct FactorArgs {
     int mean_mode;
     double tau;
     int64_t W;            // work items: w -> design w % n_designs, parameter row w / n_designs
+    int twonu;            // 1-D Matern kinds: 2 nu (integer), and 1/(Gamma(nu) 2^(nu-1))
+    double mnorm;
     double span2[MAXD];   // squared coordinate ranges of the design (bounds the exponents)
     int force_clamp;      // 1 when span2 is unknown (per-candidate designs)
     int num_sm;               // CTAs co-resident on one SM are blockIdx = s, s+num_sm, ..: each takes a
@@ -211,6 +225,16 @@ __device__ inline void load_params(const FactorArgs& A, int64_t pi, Prm* prm) {
         rho = t2 / t1;
     }
     double w = p * p + (1.0 - p) * (1.0 - p);
+    prm->kind = 0;
+    prm->w = w;
+    if (A.family >= FAM_MATERN1D) {
+        const double sn = sqrt(2.0 * A.twonu);                  // 2 sqrt(nu) = sqrt(4 nu) = sqrt(2 * twonu)
+        prm->kind = (A.family == FAM_MATERN1D) ? 1 : 2;
+        prm->c1 = sn / prm->wts[0];
+        prm->c2 = (prm->kind == 1) ? sn / (rho * prm->wts[0]) : 1.0 / (rho * prm->wts[0]);
+        prm->twonu = A.twonu;
+        prm->mnorm = A.mnorm;
+    }
     prm->rho = rho;
     prm->a = p * p / w;
     prm->b = (1.0 - p) * (1.0 - p) / w;
@@ -241,6 +265,22 @@ __device__ __forceinline__ void build_panel(const FactorArgs& A, double* Ls, con
     const int H = npad - 8 * J;
     double* pan = Ls + blk_base(J, npad);
     const int gw = gt >> 5, gnw = gsz >> 5, lane = gt & 31;
+    if (prm->kind != 0) {
+        // 1-D Matern / spline components ([D1]:368-374, [D2]:454-462): tiny designs, plain loop
+        for (int c = gw; c < 8; c += gnw) {
+            const int j = 8 * J + c;
+            for (int r0 = lane; r0 < H; r0 += 32) {
+                const int i = 8 * J + r0;
+                double v = 0.0;
+                if (j < n) {
+                    if (i < n) v = (i == j) ? 1.0 : (i > j ? corr1d(prm, fabs(Xs[i] - Xs[j])) : 0.0);
+                    else v = (naug && i == n) ? ys[j] : ((naug && i == n + 1) ? 1.0 : 0.0);
+                }
+                pan[c * H + r0] = v;
+            }
+        }
+        return;
+    }
     const double rho = prm->rho, a = prm->a, b = prm->b;
     double wts[DT > 0 ? DT : 1];
     if (DT > 0) {
@@ -579,7 +619,7 @@ __device__ __forceinline__ FactorResult factor_candidate(const FactorArgs& A, do
                 nxt = __shfl_sync(0xffffffffu, grab, 0);
             }
             CCGP_TW(2);
-            while (*flag < J + 1 || *reinterpret_cast<volatile int*>(dn) < need) { }
+            while (*flag < J + 1 || *reinterpret_cast<volatile int*>(dn) < need) __nanosleep(64);
             __threadfence_block();
             __syncwarp();
             CCGP_TB(2);
@@ -670,7 +710,8 @@ __global__ void __launch_bounds__(TEAM * TPC, MINB) factor_kernel(const FactorAr
     const int tid = (TPC == 1) ? (int)threadIdx.x : (int)(threadIdx.x & 31);
     stage_tiletab(A.tiletab, sp.tab, lay.NJ, TEAM, tid);
     const int n = lay.n, npad = lay.npad;
-    const int fw = (A.num_sm > 0 ? (int)(blockIdx.x / A.num_sm) : 0) % (TEAM / 32);   // warp of the serial part
+    // warp of the serial part: num_sm > 0 rotates it over co-resident CTAs, num_sm < 0 fixes it to warp (-num_sm - 1)
+    const int fw = (A.num_sm > 0 ? (int)(blockIdx.x / A.num_sm) : (A.num_sm < 0 ? -A.num_sm - 1 : 0)) % (TEAM / 32);
     const int64_t w0 = (int64_t)blockIdx.x * TPC + team, wstride = (int64_t)gridDim.x * TPC;
     const int otid = fw * 32;                                                        // its lane 0 writes the outputs
 

@@ -28,6 +28,7 @@ struct PredictArgs {
     const double* candv;   // parameters of the correlation vector (NULL: same as F.cand)
     int64_t ldcv;
     int vec_family;
+    int vec_unnormalised;  // 1: r(x) = p^2 r1 + (1-p)^2 r2 without the division ([D2]:479 returns early)
     double* out_mean;      // T x S column-major
     double* out_var;
     int32_t* status;       // S
@@ -120,12 +121,17 @@ __global__ void __launch_bounds__(TEAM, MINB) predict_kernel(const PredictArgs P
                 for (int tp = 0; tp < TP; ++tp) {
                     double v = 0.0;
                     if (i < n) {
-                        double s1 = 0.0;
-                        for (int k = 0; k < d; ++k) {
-                            double df = myxn[tp * MAXD + k] - Xs[k * npx + i];
-                            s1 = fma(prmv->wts[k] * df, df, s1);
+                        if (prmv->kind != 0) {
+                            v = corr1d(prmv, fabs(myxn[tp * MAXD] - Xs[i]));
+                            if (P.vec_unnormalised) v *= prmv->w;
+                        } else {
+                            double s1 = 0.0;
+                            for (int k = 0; k < d; ++k) {
+                                double df = myxn[tp * MAXD + k] - Xs[k * npx + i];
+                                s1 = fma(prmv->wts[k] * df, df, s1);
+                            }
+                            v = fma(prmv->b, dexp_neg(prmv->rho * s1), prmv->a * dexp_neg(s1));
                         }
-                        v = fma(prmv->b, dexp_neg(prmv->rho * s1), prmv->a * dexp_neg(s1));
                     }
                     rr[m][tp] = v;
                 }

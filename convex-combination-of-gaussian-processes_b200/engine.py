@@ -12,7 +12,7 @@ import numpy as np
 from . import _capi
 from ._capi import CcgpError
 
-GAUSS_ISO, GAUSS_ANISO_LAMBDA, GAUSS_ISO_RAW2 = 0, 1, 2
+GAUSS_ISO, GAUSS_ANISO_LAMBDA, GAUSS_ISO_RAW2, MATERN1D, MATERN_SPLINE1D = 0, 1, 2, 3, 4
 NATURAL, LOGSCALE = 0, 1
 MEAN_GLS_BETA, MEAN_ZERO_PLUS_TAU2 = 0, 1
 
@@ -79,6 +79,10 @@ class Engine:
         f = C.c_double()
         self._ck(self._lib.ccgp_measure_fp64_peak(self._h, C.byref(f)))
         return f.value
+
+    def set_matern_nu(self, nu: float):
+        """Smoothness of the 1-D Matern families (integer or half-integer)."""
+        self._ck(self._lib.ccgp_set_matern_nu(self._h, float(nu)))
 
     def num_params(self, family):
         return int(self._lib.ccgp_num_params(family, self.d))

@@ -48,7 +48,7 @@ def log_prior(theta, script, prior_pars=None):
         return -psi1 - psi1 ** 2 / 2 - psi2 - psi2 ** 2 / 2 - 4 * zeta - 4 / np.exp(zeta)
     psi1, psi2 = th[:, 0], th[:, 1]
     t1, t2 = np.exp(psi1), np.exp(psi2)
-    if script in ("I", "M"):
+    if script in ("I", "M", "D1", "D2"):   # [I]:453 = [M]:450 = [D1]:636 = [D2]:597
         return -4 * psi1 - 2 / t1 - 6 * psi2 - 16 / t2
     if script == "G":
         return -4 * psi1 - 1 / t1 - 6 * psi2 - 75 / t2
@@ -58,7 +58,7 @@ def log_prior(theta, script, prior_pars=None):
     raise ValueError("unknown script %r" % (script,))
 
 
-_SCRIPT_FAMILY = {"A": GAUSS_ANISO_LAMBDA, "I": GAUSS_ISO, "M": GAUSS_ISO, "G": GAUSS_ISO, "H": GAUSS_ISO,
+_SCRIPT_FAMILY = {"A": GAUSS_ANISO_LAMBDA, "I": GAUSS_ISO, "M": GAUSS_ISO, "G": GAUSS_ISO, "H": GAUSS_ISO, "D1": 3, "D2": 4,
                   "V": GAUSS_ISO_RAW2}
 
 

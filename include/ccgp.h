@@ -49,8 +49,14 @@ enum ccgp_status {
  *   GAUSS_ISO_RAW2     (p, theta1, lambda)            [V]:414-421 (2nd component scale = lambda)
  * LOGSCALE rows are logpost's real-line vectors ([A]:435-442, [I]:435-440):
  *   iso (psi1, psi2, phi), aniso (psi_1..psi_d, phi, zeta); the kernel applies
- *   theta=exp(psi), p=1/(1+exp(-phi)), lambda=exp(zeta). */
-enum ccgp_family { CCGP_GAUSS_ISO = 0, CCGP_GAUSS_ANISO_LAMBDA = 1, CCGP_GAUSS_ISO_RAW2 = 2 };
+ *   theta=exp(psi), p=1/(1+exp(-phi)), lambda=exp(zeta).
+ *   MATERN1D           (p, theta1, theta2)  1-D only: both components Matern(nu)
+ *                      "1D Combined GP Public.R":348-374, 577-584 (Matern.corr.func, Mixed.corr.matrix)
+ *   MATERN_SPLINE1D    (p, theta1, theta2)  1-D only: Matern(nu, theta1) + cubic spline (support theta2)
+ *                      "1D Combined GP Two Families Public.R":346-369, 454-462 (corr.matrix.combined)
+ *   (real-line rows as for GAUSS_ISO; nu via ccgp_set_matern_nu, default 5 as at [D1]:1080) */
+enum ccgp_family { CCGP_GAUSS_ISO = 0, CCGP_GAUSS_ANISO_LAMBDA = 1, CCGP_GAUSS_ISO_RAW2 = 2,
+                   CCGP_MATERN1D = 3, CCGP_MATERN_SPLINE1D = 4 };
 enum ccgp_scale { CCGP_NATURAL = 0, CCGP_LOGSCALE = 1 };
 /* GLS_BETA: dmnorm(y, beta.MLE, c R) as in logpost [A]:452-455.
  * ZERO_PLUS_TAU2: dmnorm(y, 0, c R + tau^2 11') as in cond.like [V]:564-575. */
@@ -64,6 +70,8 @@ int ccgp_create(ccgp_ctx** ctx, int device);
 int ccgp_destroy(ccgp_ctx* ctx);
 const char* ccgp_last_error(const ccgp_ctx* ctx); /* ctx may be NULL: last create error */
 int ccgp_sync(ccgp_ctx* ctx);
+/* Matern smoothness nu of the 1-D families (integer or half-integer, 0 < nu <= 50; default 5) */
+int ccgp_set_matern_nu(ccgp_ctx* ctx, double nu);
 /* run on the caller's CUDA stream (a cudaStream_t; NULL = the legacy default stream)
  * so the caller's events bracket the kernels; ccgp_use_own_stream goes back to the
  * context's private non-blocking stream */

@@ -38,6 +38,9 @@ EPS = np.finfo(np.float64).eps
 FAMILY_ISO = 0           # [I]:400-407  params (p, theta1, theta2)
 FAMILY_ANISO_LAMBDA = 1  # [A]:399-406  params (p, theta_1..theta_d, lambda)
 FAMILY_ISO_RAW2 = 2      # [V]:414-421  params (p, theta1, lambda): R2 uses `lambda` as its scale
+FAMILY_MATERN1D = 3      # [D1] "1D Combined GP Public.R":577-584          params (p, theta1, theta2), both Matern(nu)
+FAMILY_MATERN_SPLINE1D = 4  # [D2] "1D ... Two Families Public.R":454-462  Matern(nu, theta1) + cubic spline(theta2)
+MATERN_NU = 5.0          # [D1]:1080, [D2]:1027
 
 
 # --------------------------------------------------------------------------
@@ -80,6 +83,30 @@ def corr_vec_ISO(x, X, theta):
     return corr_vec(x, X, np.full(X.shape[1], float(theta)))
 
 
+def Matern_corr_func(nu, h, theta):
+    """[D1]:348-351: (2 sqrt(nu)|h|/theta)^nu K_nu(.) / (Gamma(nu) 2^(nu-1)), 1 at h == 0 (vectorised)."""
+    from scipy.special import kv, gamma
+    h = np.abs(np.asarray(h, dtype=np.float64))
+    t = 2.0 * math.sqrt(nu) * h / theta
+    with np.errstate(invalid="ignore", divide="ignore", over="ignore"):
+        v = t ** nu * kv(nu, t) / (gamma(nu) * 2.0 ** (nu - 1.0))
+    return np.where(h == 0, 1.0, v)
+
+
+def spline_corr_func(theta, h):
+    """[D2]:346-357: nonnegative cubic spline with support theta (vectorised)."""
+    u = np.abs(np.asarray(h, dtype=np.float64)) / theta
+    return np.where(u <= 0.5, 1 - 6 * u ** 2 + 6 * u ** 3, np.where(u <= 1.0, 2 * (1 - u) ** 3, 0.0))
+
+
+def _mixed_1d(U, family, params, nu, normalise=True):
+    p, t1, t2 = np.asarray(params, dtype=np.float64).reshape(-1)[:3]
+    R1 = Matern_corr_func(nu, U, t1)
+    R2 = Matern_corr_func(nu, U, t2) if family == FAMILY_MATERN1D else spline_corr_func(t2, U)
+    out = p ** 2 * R1 + (1 - p) ** 2 * R2
+    return out / (p ** 2 + (1 - p) ** 2) if normalise else out
+
+
 def component_scales(family, params, d):
     """Map one natural-scale parameter row to (p, theta_comp1[d], theta_comp2[d]).
 
@@ -102,6 +129,10 @@ def Mixed_corr_matrix(D, family, params):
     """[A]:399-406 / [I]:400-407 / [V]:414-421:
     R = (p^2 R1 + (1-p)^2 R2) / (p^2 + (1-p)^2)."""
     D = np.asarray(D, dtype=np.float64)
+    if family in (FAMILY_MATERN1D, FAMILY_MATERN_SPLINE1D):
+        # [D1]:368-374 corr.matrix / [D2]:454-462 corr.matrix.combined: U = |A - t(A)|
+        x = D.reshape(-1)
+        return _mixed_1d(np.abs(x[None, :] - x[:, None]), family, params, MATERN_NU)
     p, t1, t2 = component_scales(family, params, D.shape[1])
     R1 = corr_matrix(D, t1)
     R2 = corr_matrix(D, t2)
@@ -111,6 +142,10 @@ def Mixed_corr_matrix(D, family, params):
 def Mixed_corr_vec(x_new, D, family, params):
     """[A]:416-422 / [I]:417-423."""
     D = np.asarray(D, dtype=np.float64)
+    if family in (FAMILY_MATERN1D, FAMILY_MATERN_SPLINE1D):
+        # [D1]:383-389,... Mixed.corr.vec; [D2]:472-480 corr.vec.combined RETURNS BEFORE DIVIDING (quirk Q3)
+        U = np.abs(float(np.asarray(x_new).reshape(-1)[0]) - D.reshape(-1))
+        return _mixed_1d(U, family, params, MATERN_NU, normalise=(family == FAMILY_MATERN1D))
     p, t1, t2 = component_scales(family, params, D.shape[1])
     c1 = corr_vec(x_new, D, t1)
     c2 = corr_vec(x_new, D, t2)
@@ -241,7 +276,7 @@ def transform_theta(family, theta, d):
     real-line vector (psi_1.., phi[, zeta]) -> natural (p, theta.., [lambda])
     ISO / ISO_RAW2: theta = (psi1, psi2, phi);  ANISO: (psi_1..psi_d, phi, zeta)."""
     theta = np.asarray(theta, dtype=np.float64).reshape(-1)
-    if family in (FAMILY_ISO, FAMILY_ISO_RAW2):
+    if family != FAMILY_ANISO_LAMBDA:
         psi1, psi2, phi = theta[:3]
         return np.array([1.0 / (1.0 + math.exp(-phi)), math.exp(psi1), math.exp(psi2)])
     psi = theta[:d]
@@ -253,7 +288,7 @@ def transform_theta(family, theta, d):
 def log_jacobian(family, theta, d):
     """[A]:459 / [I]:452: -phi - 2 log(1+e^-phi) + sum(psi) [+ zeta]."""
     theta = np.asarray(theta, dtype=np.float64).reshape(-1)
-    if family in (FAMILY_ISO, FAMILY_ISO_RAW2):
+    if family != FAMILY_ANISO_LAMBDA:
         psi1, psi2, phi = theta[:3]
         return -phi - 2.0 * math.log(1.0 + math.exp(-phi)) + psi1 + psi2
     psi = theta[:d]
@@ -271,7 +306,7 @@ def log_prior(script, theta, prior_pars=None):
         return -psi1 - psi1 ** 2 / 2 - psi2 - psi2 ** 2 / 2 - 4 * zeta - 4 / math.exp(zeta)
     psi1, psi2 = theta[0], theta[1]
     t1, t2 = math.exp(psi1), math.exp(psi2)
-    if script == "I":
+    if script in ("I", "D1", "D2"):      # [I]:453 = [D1]:636 = [D2]:597
         return -4 * psi1 - 2 / t1 - 6 * psi2 - 16 / t2
     if script == "G":
         return -4 * psi1 - 1 / t1 - 6 * psi2 - 75 / t2
@@ -296,13 +331,9 @@ def loglik_minimal(D, y, sigma2, family, params, mean_mode="gls", tau=0.0):
     D = np.asarray(D, dtype=np.float64)
     y = np.asarray(y, dtype=np.float64).reshape(-1)
     n, d = D.shape
-    p, t1, t2 = component_scales(family, params, d)
+    p = float(np.asarray(params).reshape(-1)[0])
     w = p ** 2 + (1 - p) ** 2
-    diff = D[:, None, :] - D[None, :, :]
-    s1 = (diff ** 2 * t1).sum(axis=2)
-    s2 = (diff ** 2 * t2).sum(axis=2)
-    R = (p ** 2 / w) * np.exp(-s1) + ((1 - p) ** 2 / w) * np.exp(-s2)
-    np.fill_diagonal(R, 1.0)
+    R = Mixed_corr_matrix_direct(D, family, params)
     L, info = lapack.dpotrf(R, lower=1)
     if info != 0:
         return dict(loglik=float("nan"), beta=float("nan"), status=1)
@@ -463,6 +494,8 @@ def subset_logdet(pool, idx, family, params):
 def Mixed_corr_matrix_direct(D, family, params):
     """Direct-difference form of the mixed Gram (exact symmetry, unit diagonal)."""
     D = np.asarray(D, dtype=np.float64)
+    if family in (FAMILY_MATERN1D, FAMILY_MATERN_SPLINE1D):
+        return Mixed_corr_matrix(D, family, params)
     p, t1, t2 = component_scales(family, params, D.shape[1])
     w = p ** 2 + (1 - p) ** 2
     diff = D[:, None, :] - D[None, :, :]

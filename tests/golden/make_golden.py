@@ -197,6 +197,23 @@ def main():
         G["sub_idx_%d" % m_] = idx
         G["sub_logdet_%d" % m_] = np.array([orc.subset_logdet(lhs, ix, orc.FAMILY_ANISO_LAMBDA, par) for ix in idx])
 
+    # ---- C0: the 1-D scripts (n = 8, nu = 5): Matern+Matern and Matern+spline ------------
+    rng = np.random.default_rng(8)
+    X1 = D["design1d"][3].reshape(-1, 1)                       # one of the shipped 8-point designs
+    y1 = np.sin(2 * np.pi * X1[:, 0]) + 0.5 * np.cos(9 * X1[:, 0])
+    B = 16
+    # the scripts' priors (theta1 ~ IG(3,2), theta2 ~ IG(5,16)) put most mass where an 8-point Matern(5) Gram
+    # matrix has kappa > 1e10; the parity rows use shorter ranges so that kappa_1(R) <= 1e6 (stated gate)
+    nat1 = np.column_stack([rng.uniform(0.1, 0.9, B), rng.uniform(0.04, 0.2, B), rng.uniform(0.08, 0.4, B)])
+    Xn1 = np.linspace(0, 1, 11).reshape(-1, 1)
+    G.update({"d1_X": X1, "d1_y": y1, "d1_nat": nat1, "d1_Xnew": Xn1})
+    for tag, fam in (("d1mm", orc.FAMILY_MATERN1D), ("d1ms", orc.FAMILY_MATERN_SPLINE1D)):
+        r = nll_case(X1, y1, 0.8, fam, nat1, "gls", 0.0, 0)
+        G.update({tag + "_" + k: v for k, v in r.items()})
+        m, v = orc.predict_table(X1, y1, 0.8, fam, nat1[:4], Xn1)
+        G.update({tag + "_pred_mean": m, tag + "_pred_var": v})
+        G[tag + "_R"] = orc.Mixed_corr_matrix(X1, fam, nat1[0])
+
     np.savez_compressed(os.path.join(OUT, "golden_cases.npz"), **G)
     print("wrote", len(D), "design arrays and", len(G), "golden arrays")
     for k in ("c1n100", "c1n14", "c1n14gls", "c2gls", "c2tau", "gv50", "gv90"):

@@ -378,3 +378,41 @@ def test_large_n_vs_oracle(engine, n):
         assert rel_err(-nll[b], m["loglik"]) < TOL
         assert rel_err(-nll[b], o["loglik"]) < TOL
         assert rel_err(beta[b], m["beta"]) < 1e-9
+
+
+# ---------------------------------------------------------------- 1-D families
+@pytest.mark.parametrize("tag,family,ofam", [("d1mm", ccgp_b200.MATERN1D, orc.FAMILY_MATERN1D),
+                                             ("d1ms", ccgp_b200.MATERN_SPLINE1D, orc.FAMILY_MATERN_SPLINE1D)])
+def test_one_dimensional_families(engine, golden, tag, family, ofam):
+    """The 1-D scripts' Matern(nu=5)+Matern and Matern+cubic-spline models on a shipped 8-point design:
+    likelihood, beta, correlation matrix and the prediction table (with [D2]:479's un-normalised r)."""
+    X, y, nat = golden["d1_X"], golden["d1_y"], golden["d1_nat"]
+    engine.set_matern_nu(5.0)
+    engine.set_design(X, y)
+    nll, beta, st = engine.nll_batch(nat, family, 0.8)
+    ok = golden[tag + "_kappa"] <= 1e6
+    assert ok.sum() >= 8 and np.all(st[ok] == 0)
+    assert rel_err(-nll[ok], golden[tag + "_ref"][ok]).max() < TOL
+    assert rel_err(beta[ok], golden[tag + "_beta"][ok]).max() < 1e-9
+    R = engine.mixed_corr(nat[0], family, X)
+    assert np.abs(R - golden[tag + "_R"]).max() < 1e-14
+    m, v, _ = engine.predict(nat[:4], family, golden["d1_Xnew"], 0.8)
+    assert rel_err(m, golden[tag + "_pred_mean"]).max() < 1e-9
+    assert np.abs(v - golden[tag + "_pred_var"]).max() < 1e-8
+    # real-line rows through the wrapper (prior line shared by [D1]:636 and [D2]:597)
+    th = np.column_stack([np.log(nat[:, 1]), np.log(nat[:, 2]), np.log(nat[:, 0] / (1 - nat[:, 0]))])
+    r = api.logpost_batch(X, th[:4], y, 0.8, script="D1" if family == ccgp_b200.MATERN1D else "D2", engine=engine)
+    for b in range(4):
+        o = orc.logpost(X, th[b], y, 0.8, ofam, "D1")
+        if golden[tag + "_kappa"][b] <= 1e6:
+            assert rel_err(r["val"][b], o["val"]) < TOL
+    # half-integer smoothness goes through the closed-form branch
+    engine.set_matern_nu(2.5)
+    orc.MATERN_NU = 2.5
+    try:
+        nll25, _, _ = engine.nll_batch(nat[:4], family, 0.8)
+        for b in range(4):
+            assert rel_err(-nll25[b], orc.loglik_minimal(X, y, 0.8, ofam, nat[b])["loglik"]) < 1e-9
+    finally:
+        orc.MATERN_NU = 5.0
+        engine.set_matern_nu(5.0)

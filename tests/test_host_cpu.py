@@ -171,3 +171,38 @@ int main(){ double worst=0; srand(1);
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0
     assert float(out.stdout) < 3.4e-16
+
+
+def test_bessel_matern_spline_host_accuracy(tmp_path):
+    """ccgp_math.h's K0/K1-based Matern and the cubic spline (the code the kernels run) vs SciPy's kv."""
+    from scipy.special import kv, gamma
+    src = tmp_path / "b.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include "%s/convex-combination-of-gaussian-processes_b200/csrc/ccgp_math.h"
+int main(){ for (int i = 0; i < 400; ++i) { double t = 1e-4 * pow(1.04, i); double k0, k1; ccgp_bessel_k01(t, &k0, &k1);
+  printf("%%.17g %%.17g %%.17g %%.17g %%.17g %%.17g\n", t, k0, k1, ccgp_matern(t, 10, 1.0/384.0),
+         ccgp_matern(t, 5, 1.0/(1.3293403881791370*2.8284271247461903)), ccgp_spline(t)); } return 0; }
+''' % ROOT)
+    exe = tmp_path / "b"
+    subprocess.check_call(["gcc", "-O2", "-mfma", "-o", str(exe), str(src), "-lm"])
+    rows = np.array([[float(v) for v in line.split()] for line in subprocess.run([str(exe)], capture_output=True, text=True).stdout.splitlines()])
+    t = rows[:, 0]
+    ok = t < 600
+    assert np.max(np.abs(rows[ok, 1] / kv(0, t[ok]) - 1)) < 5e-15
+    assert np.max(np.abs(rows[ok, 2] / kv(1, t[ok]) - 1)) < 5e-15
+    for col, nu in ((3, 5.0), (4, 2.5)):
+        want = t ** nu * kv(nu, t) / (gamma(nu) * 2 ** (nu - 1))
+        assert np.max(np.abs(rows[ok, col] - want[ok]) / np.maximum(want[ok], 1e-300)) < 2e-14
+    assert np.allclose(rows[:, 5], orc.spline_corr_func(1.0, t), rtol=0, atol=1e-16)
+
+
+def test_oracle_matern_half_integer_closed_forms():
+    h = np.linspace(0.0, 2.0, 41)
+    for theta in (0.3, 1.7):
+        t = 2 * np.sqrt(0.5) * h / theta
+        assert np.allclose(orc.Matern_corr_func(0.5, h, theta), np.exp(-t), rtol=1e-13)
+        t = 2 * np.sqrt(1.5) * h / theta
+        assert np.allclose(orc.Matern_corr_func(1.5, h, theta), (1 + t) * np.exp(-t), rtol=1e-13)
+    R = orc.Mixed_corr_matrix(np.linspace(0, 1, 8).reshape(-1, 1), orc.FAMILY_MATERN_SPLINE1D, [0.4, 0.3, 0.5])
+    assert np.allclose(R, R.T) and np.allclose(np.diag(R), 1.0)
