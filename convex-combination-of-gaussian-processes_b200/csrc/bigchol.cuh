@@ -17,24 +17,9 @@
 #pragma once
 #include <algorithm>
 #include "factor_engine.cuh"
+#include "bigchol_ws.h"
 
 namespace ccgp {
-
-struct BigCholWorkspace {
-    double* A = nullptr;       // chunk * nrp * ncp
-    double* logdet = nullptr;  // chunk
-    int* bad = nullptr;        // chunk
-    Prm* prm = nullptr;        // chunk
-    size_t bytesA = 0;
-    int cap = 0;
-    void release() {
-        if (A) cudaFree(A);
-        if (logdet) cudaFree(logdet);
-        if (bad) cudaFree(bad);
-        if (prm) cudaFree(prm);
-        A = nullptr; logdet = nullptr; bad = nullptr; prm = nullptr; bytesA = 0; cap = 0;
-    }
-};
 
 struct BigArgs {
     double* A;

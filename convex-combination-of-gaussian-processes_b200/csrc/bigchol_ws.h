@@ -1,0 +1,24 @@
+// bigchol_ws.h -- device workspace of the large-n blocked path (bigchol.cuh), owned by the context
+#pragma once
+#include <cuda_runtime.h>
+#include "factor_engine.cuh"
+
+namespace ccgp {
+
+struct BigCholWorkspace {
+    double* A = nullptr;       // chunk * nrp * ncp
+    double* logdet = nullptr;  // chunk
+    int* bad = nullptr;        // chunk
+    Prm* prm = nullptr;        // chunk
+    size_t bytesA = 0;
+    int cap = 0;
+    void release() {
+        if (A) cudaFree(A);
+        if (logdet) cudaFree(logdet);
+        if (bad) cudaFree(bad);
+        if (prm) cudaFree(prm);
+        A = nullptr; logdet = nullptr; bad = nullptr; prm = nullptr; bytesA = 0; cap = 0;
+    }
+};
+
+}  // namespace ccgp

@@ -10,99 +10,21 @@
 #include <vector>
 #include <algorithm>
 #include "../../include/ccgp.h"
-#include "factor_engine.cuh"
+#include "ccgp_ctx.h"
 #include "predict_kernel.cuh"
 #include "me_kernel.cuh"
 #include "bigchol.cuh"
 
 using namespace ccgp;
 
-struct ccgp_ctx {
-    int device = 0;
-    int num_sm = 0;
-    int max_smem_optin = 0;
-    cudaStream_t stream = nullptr;
-    cudaStream_t own_stream = nullptr;
-    int n = 0, d = 0;
-    double* d_X = nullptr;
-    double* d_y = nullptr;
-    double span2[MAXD] = {0};   // squared coordinate ranges of the shared design
-    int twonu = 10;             // Matern smoothness of the 1-D families, 2*nu (reference default nu = 5)
-    double mnorm = 1.0 / 384.0; // 1 / (Gamma(nu) 2^(nu-1))
-    std::map<std::vector<int>, uint32_t*> tiletabs;   // (n, naug, TR, TC) -> tile table
-    void* ws = nullptr;       // device workspace for the host-pointer entry points
-    size_t ws_bytes = 0;
-    void* ws2 = nullptr;      // small device workspace (params, reductions)
-    size_t ws2_bytes = 0;
-    char err[512] = {0};
-    int64_t launches = 0;
-    int last_team = 0, last_smem = 0, last_ctas = 0, last_variant = -1;
-    BigCholWorkspace big;
-    long long* dbg = nullptr;  // phase-timing buffer (debug)
-};
-
 static char g_create_err[512] = "";
-
-#define CK(call)                                                                                   \
-    do {                                                                                           \
-        cudaError_t e_ = (call);                                                                   \
-        if (e_ != cudaSuccess) {                                                                   \
-            snprintf(ctx->err, sizeof(ctx->err), "%s:%d %s: %s", __FILE__, __LINE__, #call,        \
-                     cudaGetErrorString(e_));                                                      \
-            return CCGP_ERR_CUDA;                                                                  \
-        }                                                                                          \
-    } while (0)
-
-#define RC(call)                                                                                   \
-    do {                                                                                           \
-        int rc_ = (call);                                                                          \
-        if (rc_) return rc_;                                                                       \
-    } while (0)
-
-#define ARG(cond)                                                                                  \
-    do {                                                                                           \
-        if (!(cond)) {                                                                             \
-            snprintf(ctx->err, sizeof(ctx->err), "bad argument: %s", #cond);                       \
-            return CCGP_ERR_ARG;                                                                   \
-        }                                                                                          \
-    } while (0)
-
-static int env_int(const char* name, int dflt) {
-    const char* s = getenv(name);
-    return (s && *s) ? atoi(s) : dflt;
-}
-
-// ------------------------------------------------------------------ variants
-typedef void (*factor_fn)(const FactorArgs);
-struct Variant { int team, tr, tc, minb, tpc; factor_fn fn_d0, fn_d2; };
-
-#define CCGP_VARIANTS(X)                                                                           \
-    X(32, 4, 4, 16) X(32, 8, 4, 16) X(64, 4, 4, 8) X(64, 8, 4, 8) X(64, 4, 8, 8) X(128, 4, 4, 4)      \
-    X(128, 8, 4, 4) X(128, 4, 8, 4) X(256, 4, 4, 4) X(256, 4, 4, 2) X(32, 8, 4, 4) X(32, 4, 4, 4)   \
-    X(32, 8, 8, 4) X(96, 4, 4, 5) X(64, 8, 4, 4) X(128, 4, 4, 5)                                   \
-    Y(4, 4, 4) Y(8, 4, 4) Y(4, 4, 2) Y(4, 4, 3) Y(4, 8, 4)
-
-#define X(T, R, K, M) {T, R, K, M, 1, factor_kernel<T, R, K, 0, M, 1>, factor_kernel<T, R, K, 2, M, 1>},
-#define Y(R, K, P) {32, R, K, 1, P, factor_kernel<32, R, K, 0, 1, P>, factor_kernel<32, R, K, 2, 1, P>},
-static const Variant g_variants[] = {CCGP_VARIANTS(X)};
-#undef X
-#undef Y
-static const int g_num_variants = sizeof(g_variants) / sizeof(g_variants[0]);
-
-static int default_variant(const Layout& l) {
-    // measured on B200 (profiles/r01_tune_variants_v3.json): one warp per candidate wins while many
-    // CTAs fit per SM; 4 warps once shared memory caps residency at ~4 candidates per SM
-    if (l.npad <= 72) return 0;    // 32 threads, 4x4 tiles
-    if (l.npad <= 136) return 5;   // 128 threads, 4x4 tiles
-    return 9;                      // 256 threads, 4x4 tiles (1-2 candidates resident per SM)
-}
 
 // tile table of the trailing-matrix updates: [NJ+1] first-tile index per block column, then one
 // packed entry per TR x TC tile, ordered by block column.  Within a column group (TC columns
 // of block column Jc, rows 8Jc..npad-1) tile t owns the TR/2 row pairs t, t+Nt, t+2Nt, ..
 // (Nt = tiles of the group), so consecutive tiles touch consecutive 16-byte words.
 // entry = first row | (row distance between the tile's pairs) << 10 | first column << 20
-static int get_tiletab(ccgp_ctx* ctx, const Layout& l, int TR, int TC, const uint32_t** out) {
+int get_tiletab(ccgp_ctx* ctx, const Layout& l, int TR, int TC, const uint32_t** out) {
     std::vector<int> key = {l.n, l.naug, TR, TC};
     auto it = ctx->tiletabs.find(key);
     if (it != ctx->tiletabs.end()) { *out = it->second; return 0; }
@@ -149,42 +71,6 @@ static int ensure_ws2(ccgp_ctx* ctx, size_t bytes) {
     size_t want = std::max(bytes, (size_t)1 << 16);
     CK(cudaMalloc(&ctx->ws2, want));
     ctx->ws2_bytes = want;
-    return 0;
-}
-
-// choose variant + grid and launch the factor kernel
-static int launch_factor(ccgp_ctx* ctx, FactorArgs& A) {
-    const Layout& l = A.lay;
-    int v = env_int("CCGP_VARIANT", -1);
-    if (v < 0 || v >= g_num_variants) v = default_variant(l);
-    const size_t team_smem = (smem_bytes(l, A.d) + 15) / 16 * 16;
-    if (team_smem > (size_t)ctx->max_smem_optin) {
-        snprintf(ctx->err, sizeof(ctx->err), "n=%d needs %zu B shared memory (> %d)", l.n, team_smem, ctx->max_smem_optin);
-        return CCGP_ERR_UNSUPPORTED;
-    }
-    if (g_variants[v].tpc > 1 && team_smem * g_variants[v].tpc > (size_t)ctx->max_smem_optin) v = default_variant(l);
-    const Variant& var = g_variants[v];
-    const size_t smem = team_smem * var.tpc;
-    A.team_smem_bytes = (int64_t)team_smem;
-    factor_fn fn = (A.d == 2) ? var.fn_d2 : var.fn_d0;
-    if (env_int("CCGP_NO_DT", 0)) fn = var.fn_d0;
-    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int nb = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, var.team * var.tpc, smem));
-    if (nb < 1) { snprintf(ctx->err, sizeof(ctx->err), "kernel variant %d does not fit", v); return CCGP_ERR_UNSUPPORTED; }
-    { int cap = env_int("CCGP_CTAS_PER_SM", 0); if (cap > 0 && cap < nb) nb = cap; }
-    int64_t grid = (int64_t)nb * ctx->num_sm;
-    if (grid * var.tpc > A.W) grid = (A.W + var.tpc - 1) / var.tpc;
-    if (grid < 1) return 0;
-    A.dbg = ctx->dbg;
-    A.num_sm = env_int("CCGP_ROTATE", 0) ? ctx->num_sm : 0;    // rotation measured no better than warp 0 (profiles/)
-    if (env_int("CCGP_FW", -1) >= 0) A.num_sm = -(env_int("CCGP_FW", 0) + 1);
-    A.debug_stop = env_int("CCGP_DEBUG_STOP", 0);
-    RC(get_tiletab(ctx, l, var.tr, var.tc, &A.tiletab));
-    fn<<<(unsigned)grid, var.team * var.tpc, smem, ctx->stream>>>(A);
-    CK(cudaGetLastError());
-    ctx->launches++;
-    ctx->last_team = var.team; ctx->last_smem = (int)smem; ctx->last_ctas = nb; ctx->last_variant = v;
     return 0;
 }
 
@@ -242,6 +128,7 @@ extern "C" int ccgp_destroy(ccgp_ctx* ctx) {
     if (ctx->d_y) cudaFree(ctx->d_y);
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->ws2) cudaFree(ctx->ws2);
+    if (ctx->sm_slots) cudaFree(ctx->sm_slots);
     ctx->big.release();
     cudaStreamDestroy(ctx->own_stream);
     delete ctx;

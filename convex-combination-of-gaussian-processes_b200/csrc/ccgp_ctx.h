@@ -1,0 +1,77 @@
+// ccgp_ctx.h -- the context object and host-side helpers shared by the translation units of libccgp.so
+#pragma once
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdint.h>
+#include <map>
+#include <vector>
+#include <algorithm>
+#include "../../include/ccgp.h"
+#include "factor_engine.cuh"
+#include "bigchol_ws.h"
+
+using namespace ccgp;
+
+struct ccgp_ctx {
+    int device = 0;
+    int num_sm = 0;
+    int max_smem_optin = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;
+    int n = 0, d = 0;
+    double* d_X = nullptr;
+    double* d_y = nullptr;
+    double span2[MAXD] = {0};   // squared coordinate ranges of the shared design
+    int twonu = 10;             // Matern smoothness of the 1-D families, 2*nu (reference default nu = 5)
+    double mnorm = 1.0 / 384.0; // 1 / (Gamma(nu) 2^(nu-1))
+    std::map<std::vector<int>, uint32_t*> tiletabs;   // (n, naug, TR, TC) -> tile table
+    void* ws = nullptr;       // device workspace for the host-pointer entry points
+    size_t ws_bytes = 0;
+    void* ws2 = nullptr;      // small device workspace (params, reductions)
+    size_t ws2_bytes = 0;
+    char err[512] = {0};
+    int64_t launches = 0;
+    int last_team = 0, last_smem = 0, last_ctas = 0, last_variant = -1;
+    BigCholWorkspace big;
+    long long* dbg = nullptr;  // phase-timing buffer (debug)
+    int* sm_slots = nullptr;   // per-SM CTA arrival counters of the DMMA kernel
+};
+
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            snprintf(ctx->err, sizeof(ctx->err), "%s:%d %s: %s", __FILE__, __LINE__, #call,        \
+                     cudaGetErrorString(e_));                                                      \
+            return CCGP_ERR_CUDA;                                                                  \
+        }                                                                                          \
+    } while (0)
+
+#define RC(call)                                                                                   \
+    do {                                                                                           \
+        int rc_ = (call);                                                                          \
+        if (rc_) return rc_;                                                                       \
+    } while (0)
+
+#define ARG(cond)                                                                                  \
+    do {                                                                                           \
+        if (!(cond)) {                                                                             \
+            snprintf(ctx->err, sizeof(ctx->err), "bad argument: %s", #cond);                       \
+            return CCGP_ERR_ARG;                                                                   \
+        }                                                                                          \
+    } while (0)
+
+inline int env_int(const char* name, int dflt) {
+    const char* s = getenv(name);
+    return (s && *s) ? atoi(s) : dflt;
+}
+
+
+typedef void (*factor_fn)(const FactorArgs);
+int get_tiletab(ccgp_ctx* ctx, const Layout& l, int TR, int TC, const uint32_t** out);
+// factor_launch.cu / factor_mma_launch.cu
+int launch_factor(ccgp_ctx* ctx, FactorArgs& A);
+int launch_factor_mma(ccgp_ctx* ctx, FactorArgs& A, int* launched);

@@ -162,6 +162,8 @@ struct FactorArgs {
     int64_t team_smem_bytes;  // shared bytes of one team (several one-warp teams may share a CTA)
     int debug_stop;       // debug: 1 = stop after the build phase (tools/occupancy_probe.py)
     long long* dbg;       // optional phase-timing buffer (tools/phase_timing.py); NULL in production
+    int* sm_slots;        // DMMA kernel: per-SM arrival counters (zeroed before the launch) -> CTA slot on its SM
+    int nparams;          // parameters per candidate row (ccgp_num_params)
     double* out0;         // NLL: nll          DET: log det (all pivots)
     double* out1;         // NLL: beta         DET: log det (tail pivots)
     double* out2;         // DET: -det(tail) (negated determinant, the ME criterion value)
@@ -193,9 +195,8 @@ __device__ __forceinline__ void prod_accum(double& mant, int& es, double piv) {
     mant = __hiloint2double(hi - (e << 20), __double2loint(mant));
 }
 
-__device__ inline void load_params(const FactorArgs& A, int64_t pi, Prm* prm) {
-    const double* c = A.cand + pi;
-    const int64_t ld = A.ldc;
+// `c`/`ld`: the candidate's parameter row (element k at c[k*ld]) -- global memory, or a staged copy
+__device__ inline void load_params_from(const FactorArgs& A, const double* c, const int64_t ld, Prm* prm) {
     const int d = A.d;
     double p, rho;
     if (A.family == FAM_ANISO) {
@@ -243,7 +244,10 @@ __device__ inline void load_params(const FactorArgs& A, int64_t pi, Prm* prm) {
     double smax = 0.0;
     for (int k = 0; k < d; ++k) smax += prm->wts[k] * A.span2[k];
     smax *= fmax(rho, 1.0);
-    prm->clamp = (A.force_clamp || !(smax < 1e8)) ? 1 : 0;
+    prm->clamp = (A.force_clamp || !(smax < 1e6)) ? 1 : 0;   // 1e6: the table-driven exp's int32 range
+}
+__device__ inline void load_params(const FactorArgs& A, int64_t pi, Prm* prm) {
+    load_params_from(A, A.cand + pi, A.ldc, prm);
 }
 
 struct FactorResult {  // valid in thread 0 of the team after factor_candidate()
