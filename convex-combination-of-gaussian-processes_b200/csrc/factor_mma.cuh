@@ -94,7 +94,8 @@ __device__ __forceinline__ void mma_build(const FactorArgs& A, double* Ls, const
             for (int k = 0; k < DT; ++k) { xj0[k] = Xs[k * npx + jc0]; xj1[k] = Xs[k * npx + jc1]; }
         }
         double* colbase = Ls + blk_base(c, npad) + 2 * lane;
-        for (int r = c + warp; r < NR; r += nwarps) {
+        // the two entries (row 8r + g, columns j0, j1) of tile (r, c)
+        auto entry = [&](int r, double& v0, double& v1) {
             const int i = 8 * r + g;
             const int ic = min(i, n - 1);
             double s0 = 0.0, s1 = 0.0;
@@ -114,22 +115,42 @@ __device__ __forceinline__ void mma_build(const FactorArgs& A, double* Ls, const
                     s1 = fma(wk * d1, d1, s1);
                 }
             }
-            double v0 = fma(b, dexp_neg_tab_dev<CLAMP>(rho * s0, T), a * dexp_neg_tab_dev<CLAMP>(s0, T));
-            double v1 = fma(b, dexp_neg_tab_dev<CLAMP>(rho * s1, T), a * dexp_neg_tab_dev<CLAMP>(s1, T));
-            if (r == c || 8 * r + 7 >= n) {                  // warp-uniform: diagonal tile or rows beyond the design
-                if (i < n) {
-                    if (j0 >= i) v0 = (j0 == i) ? 1.0 : 0.0;
-                    if (j1 >= i) v1 = (j1 == i) ? 1.0 : 0.0;
-                } else if (naug && i == n) {
-                    v0 = (j0 < n) ? ys[j0] : 0.0;
-                    v1 = (j1 < n) ? ys[j1] : 0.0;
-                } else if (naug && i == n + 1) {
-                    v0 = (j0 < n) ? 1.0 : 0.0;
-                    v1 = (j1 < n) ? 1.0 : 0.0;
-                } else {
-                    v0 = 0.0; v1 = 0.0;
-                }
+            v0 = fma(b, dexp_neg_tab_dev<CLAMP>(rho * s0, T), a * dexp_neg_tab_dev<CLAMP>(s0, T));
+            v1 = fma(b, dexp_neg_tab_dev<CLAMP>(rho * s1, T), a * dexp_neg_tab_dev<CLAMP>(s1, T));
+        };
+        // diagonal tile / rows beyond the design: unit diagonal, zero upper part, rows y' and 1', zero padding
+        auto fixup = [&](int r, double& v0, double& v1) {
+            const int i = 8 * r + g;
+            if (i < n) {
+                if (j0 >= i) v0 = (j0 == i) ? 1.0 : 0.0;
+                if (j1 >= i) v1 = (j1 == i) ? 1.0 : 0.0;
+            } else if (naug && i == n) {
+                v0 = (j0 < n) ? ys[j0] : 0.0;
+                v1 = (j1 < n) ? ys[j1] : 0.0;
+            } else if (naug && i == n + 1) {
+                v0 = (j0 < n) ? 1.0 : 0.0;
+                v1 = (j1 < n) ? 1.0 : 0.0;
+            } else {
+                v0 = 0.0; v1 = 0.0;
             }
+        };
+        int r = c + warp;
+        // two tiles per iteration: eight exponentials in flight per lane (a lone warp has nobody
+        // else to hide the table load and the FP64 latencies behind)
+        for (; r + nwarps < NR; r += 2 * nwarps) {
+            const int r2 = r + nwarps;
+            double v0, v1, u0, u1;
+            entry(r, v0, v1);
+            entry(r2, u0, u1);
+            if (r == c || 8 * r + 7 >= n) fixup(r, v0, v1);          // warp-uniform
+            if (8 * r2 + 7 >= n) fixup(r2, u0, u1);
+            st2(colbase + (r - c) * 64, v0, v1);
+            st2(colbase + (r2 - c) * 64, u0, u1);
+        }
+        if (r < NR) {
+            double v0, v1;
+            entry(r, v0, v1);
+            if (r == c || 8 * r + 7 >= n) fixup(r, v0, v1);
             st2(colbase + (r - c) * 64, v0, v1);
         }
     }

@@ -1,6 +1,7 @@
 // factor_mma_launch.cu -- variant table and launcher of the DMMA factor kernel (factor_mma.cuh)
 #include "ccgp_ctx.h"
 #include "factor_mma.cuh"
+#include "factor_warp.cuh"
 
 // ---- DMMA variants (factor_mma.cuh): NW warps per candidate, MAXT tiles per update warp ----
 struct MmaVariant { int nw, maxt; factor_fn fn_d0, fn_d2; };
@@ -9,11 +10,92 @@ static const MmaVariant g_mma_variants[] = {M(4, 2) M(4, 4) M(4, 6) M(4, 9) M(3,
 #undef M
 static const int g_num_mma_variants = sizeof(g_mma_variants) / sizeof(g_mma_variants[0]);
 
-// returns 1 when the candidate batch was launched on the DMMA kernel, 0 when it does not apply
+// ---- one-warp-per-candidate DMMA kernel (factor_warp.cuh): MAXT = tiles of the first block column, even ----
+struct WarpVariant { int maxt, minb; factor_fn fn_d0, fn_d2; };
+#define WV(MT, MB) {MT, MB, factor_warp_kernel<MT, 0, MB>, factor_warp_kernel<MT, 2, MB>},
+static const WarpVariant g_warp_variants[] = {WV(4, 3) WV(8, 2) WV(14, 1)};
+#undef WV
+
+struct PairVariant { int maxt, minb; factor_fn fn_d0, fn_d2; };
+#define PV(MT, MB) {MT, MB, factor_pair_kernel<MT, 0, MB>, factor_pair_kernel<MT, 2, MB>},
+static const PairVariant g_pair_variants[] = {PV(4, 2) PV(8, 1) PV(14, 1)};
+#undef PV
+
+static int launch_factor_pair(ccgp_ctx* ctx, FactorArgs& A, int* launched) {
+    *launched = 0;
+    const Layout& l = A.lay;
+    const int NR = l.npad / 8;
+    const PairVariant* var = nullptr;
+    for (const PairVariant& v : g_pair_variants)
+        if (NR <= v.maxt) { var = &v; break; }
+    if (!var) return 0;
+    const size_t team_smem = pair_team_smem_bytes(l, A.d);
+    const size_t smem = team_smem * PAIR_TEAMS + WARP_CTA_EXTRA;
+    if (smem > (size_t)ctx->max_smem_optin) return 0;
+    factor_fn fn = (A.d == 2) ? var->fn_d2 : var->fn_d0;
+    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int nb = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, PAIR_TEAMS * 64, smem));
+    if (nb < 1) return 0;
+    { int cap = env_int("CCGP_CTAS_PER_SM", 0); if (cap > 0 && cap < nb) nb = cap; }
+    int64_t grid = (int64_t)nb * ctx->num_sm;
+    if (grid * PAIR_TEAMS > A.W) grid = (A.W + PAIR_TEAMS - 1) / PAIR_TEAMS;
+    if (grid < 1) { *launched = 1; return 0; }
+    A.team_smem_bytes = (int64_t)team_smem;
+    A.dbg = nullptr;
+    A.nparams = (A.family == FAM_ANISO) ? A.d + 2 : 3;
+    fn<<<(unsigned)grid, PAIR_TEAMS * 64, smem, ctx->stream>>>(A);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    ctx->last_team = 64; ctx->last_smem = (int)smem; ctx->last_ctas = nb; ctx->last_variant = 300 + var->maxt;
+    *launched = 1;
+    return 0;
+}
+
+static int launch_factor_warp(ccgp_ctx* ctx, FactorArgs& A, int* launched) {
+    *launched = 0;
+    const Layout& l = A.lay;
+    const int NR = l.npad / 8;
+    const WarpVariant* var = nullptr;
+    for (const WarpVariant& v : g_warp_variants)
+        if (NR <= v.maxt) { var = &v; break; }
+    if (!var) return 0;
+    const size_t team_smem = warp_team_smem_bytes(l, A.d);
+    const size_t smem = team_smem * WARP_TEAMS + WARP_CTA_EXTRA;
+    if (smem > (size_t)ctx->max_smem_optin) return 0;
+    factor_fn fn = (A.d == 2) ? var->fn_d2 : var->fn_d0;
+    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int nb = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, WARP_TEAMS * 32, smem));
+    if (nb < 1) return 0;
+    { int cap = env_int("CCGP_CTAS_PER_SM", 0); if (cap > 0 && cap < nb) nb = cap; }
+    int64_t grid = (int64_t)nb * ctx->num_sm;
+    if (grid * WARP_TEAMS > A.W) grid = (A.W + WARP_TEAMS - 1) / WARP_TEAMS;
+    if (grid < 1) { *launched = 1; return 0; }
+    A.team_smem_bytes = (int64_t)team_smem;
+    A.dbg = ctx->dbg;
+    A.nparams = (A.family == FAM_ANISO) ? A.d + 2 : 3;
+    fn<<<(unsigned)grid, WARP_TEAMS * 32, smem, ctx->stream>>>(A);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    ctx->last_team = 32; ctx->last_smem = (int)smem; ctx->last_ctas = nb; ctx->last_variant = 200 + var->maxt;
+    *launched = 1;
+    return 0;
+}
+
+// returns 1 when the candidate batch was launched on a DMMA kernel, 0 when none applies
 int launch_factor_mma(ccgp_ctx* ctx, FactorArgs& A, int* launched) {
     *launched = 0;
     const Layout& l = A.lay;
     if (A.family >= FAM_MATERN1D || env_int("CCGP_NO_MMA", 0)) return 0;
+    if (!env_int("CCGP_NO_PAIR", 0) && l.npad >= env_int("CCGP_PAIR_MIN_NPAD", 24)) {
+        RC(launch_factor_pair(ctx, A, launched));
+        if (*launched) return 0;
+    }
+    if (!env_int("CCGP_NO_WARP", 0) && l.npad >= env_int("CCGP_WARP_MIN_NPAD", 24)) {
+        RC(launch_factor_warp(ctx, A, launched));
+        if (*launched) return 0;
+    }
     if (l.npad < env_int("CCGP_MMA_MIN_NPAD", 40)) return 0;
     const int nw = env_int("CCGP_MMA_NW", 4);
     const int NR = l.npad / 8;
