@@ -2,6 +2,7 @@
 #include "ccgp_ctx.h"
 #include "factor_mma.cuh"
 #include "factor_warp.cuh"
+#include "factor_team.cuh"
 
 // ---- DMMA variants (factor_mma.cuh): NW warps per candidate, MAXT tiles per update warp ----
 struct MmaVariant { int nw, maxt; factor_fn fn_d0, fn_d2; };
@@ -15,6 +16,48 @@ struct WarpVariant { int maxt, minb; factor_fn fn_d0, fn_d2; };
 #define WV(MT, MB) {MT, MB, factor_warp_kernel<MT, 0, MB>, factor_warp_kernel<MT, 2, MB>},
 static const WarpVariant g_warp_variants[] = {WV(4, 3) WV(8, 2) WV(14, 1)};
 #undef WV
+
+// ---- team kernel (factor_team.cuh): NW warps per candidate on one sub-partition; nrmax = most tile rows ----
+struct TeamVariant { int nw, nrmax, maxt; factor_fn fn_d0, fn_d2; };
+#define TV(NWv, NRM, MT, MB) {NWv, NRM, MT, factor_team_kernel<NWv, MT, 0, MB>, factor_team_kernel<NWv, MT, 2, MB>},
+static const TeamVariant g_team_variants[] = {
+    TV(2, 5, 4, 1) TV(2, 9, 8, 1) TV(2, 14, 13, 1)
+    TV(3, 5, 2, 1) TV(3, 9, 4, 1) TV(3, 14, 7, 1)
+    TV(4, 5, 2, 1) TV(4, 9, 3, 1) TV(4, 14, 5, 1)};
+#undef TV
+
+static int launch_factor_team(ccgp_ctx* ctx, FactorArgs& A, int* launched) {
+    *launched = 0;
+    const Layout& l = A.lay;
+    const int NR = l.npad / 8;
+    const int nw = env_int("CCGP_TEAM_NW", 3);
+    const TeamVariant* var = nullptr;
+    for (const TeamVariant& v : g_team_variants)
+        if (v.nw == nw && NR <= v.nrmax) { var = &v; break; }
+    if (!var) return 0;
+    const size_t tsm = team_smem_bytes(l, A.d);
+    const size_t smem = tsm * TEAMS_PER_CTA + TEAM_CTA_EXTRA;
+    if (smem > (size_t)ctx->max_smem_optin) return 0;
+    const int threads = TEAMS_PER_CTA * var->nw * 32;
+    factor_fn fn = (A.d == 2) ? var->fn_d2 : var->fn_d0;
+    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int nb = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, threads, smem));
+    if (nb < 1) return 0;
+    { int cap = env_int("CCGP_CTAS_PER_SM", 0); if (cap > 0 && cap < nb) nb = cap; }
+    int64_t grid = (int64_t)nb * ctx->num_sm;
+    if (grid * TEAMS_PER_CTA > A.W) grid = (A.W + TEAMS_PER_CTA - 1) / TEAMS_PER_CTA;
+    if (grid < 1) { *launched = 1; return 0; }
+    A.team_smem_bytes = (int64_t)tsm;
+    A.dbg = ctx->dbg;
+    A.nparams = (A.family == FAM_ANISO) ? A.d + 2 : 3;
+    fn<<<(unsigned)grid, threads, smem, ctx->stream>>>(A);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    ctx->last_team = var->nw * 32; ctx->last_smem = (int)smem; ctx->last_ctas = nb; ctx->last_variant = 400 + var->nw * 10;
+    *launched = 1;
+    return 0;
+}
 
 struct PairVariant { int maxt, minb; factor_fn fn_d0, fn_d2; };
 #define PV(MT, MB) {MT, MB, factor_pair_kernel<MT, 0, MB>, factor_pair_kernel<MT, 2, MB>},
@@ -42,7 +85,7 @@ static int launch_factor_pair(ccgp_ctx* ctx, FactorArgs& A, int* launched) {
     if (grid * PAIR_TEAMS > A.W) grid = (A.W + PAIR_TEAMS - 1) / PAIR_TEAMS;
     if (grid < 1) { *launched = 1; return 0; }
     A.team_smem_bytes = (int64_t)team_smem;
-    A.dbg = nullptr;
+    A.dbg = ctx->dbg;
     A.nparams = (A.family == FAM_ANISO) ? A.d + 2 : 3;
     fn<<<(unsigned)grid, PAIR_TEAMS * 64, smem, ctx->stream>>>(A);
     CK(cudaGetLastError());
@@ -83,22 +126,31 @@ static int launch_factor_warp(ccgp_ctx* ctx, FactorArgs& A, int* launched) {
     return 0;
 }
 
-// returns 1 when the candidate batch was launched on a DMMA kernel, 0 when none applies
+// returns 1 when the candidate batch was launched on a DMMA kernel, 0 when none applies.
+// Choice by tile rows NR = npad/8, measured on B200 (profiles/r01_tune_kernels.txt):
+//   NR <= 10 (n <= ~78): one warp per candidate -- shared memory lets 2-3 candidates share a sub-partition
+//   NR <= 14 (n <= ~110): three warps per candidate on one sub-partition (shared memory caps residency at 4/SM)
+//   larger: the CTA-per-candidate DMMA kernel (factor_mma.cuh), then the DFMA kernel / HBM path
 int launch_factor_mma(ccgp_ctx* ctx, FactorArgs& A, int* launched) {
     *launched = 0;
     const Layout& l = A.lay;
     if (A.family >= FAM_MATERN1D || env_int("CCGP_NO_MMA", 0)) return 0;
-    if (!env_int("CCGP_NO_PAIR", 0) && l.npad >= env_int("CCGP_PAIR_MIN_NPAD", 24)) {
+    const int NR = l.npad / 8;
+    const int kern = env_int("CCGP_KERNEL", 0);      // 0 auto, 1 warp, 2 pair, 3 team, 4 cta
+    if ((kern == 0 && NR <= 10) || kern == 1) {
+        RC(launch_factor_warp(ctx, A, launched));
+        if (*launched) return 0;
+    }
+    if (kern == 2) {
         RC(launch_factor_pair(ctx, A, launched));
         if (*launched) return 0;
     }
-    if (!env_int("CCGP_NO_WARP", 0) && l.npad >= env_int("CCGP_WARP_MIN_NPAD", 24)) {
-        RC(launch_factor_warp(ctx, A, launched));
+    if ((kern == 0 && NR <= 14) || kern == 3) {
+        RC(launch_factor_team(ctx, A, launched));
         if (*launched) return 0;
     }
     if (l.npad < env_int("CCGP_MMA_MIN_NPAD", 40)) return 0;
     const int nw = env_int("CCGP_MMA_NW", 4);
-    const int NR = l.npad / 8;
     const MmaVariant* var = nullptr;
     for (int i = 0; i < g_num_mma_variants; ++i) {
         const MmaVariant& v = g_mma_variants[i];

@@ -270,6 +270,10 @@ inline size_t pair_team_smem_bytes(const Layout& l, int d) {
     return (dbl * 8 + 2 * sizeof(Prm) + 15) / 16 * 16;
 }
 
+// phase timing (debug, tools/phase_timing_pair.py): team 0 of block 0; warp A slots 0.., warp B slots 16..
+#define CCGP_PT(slot) do { if (A.dbg && blockIdx.x == 0 && team == 0 && lane == 0) { \
+        long long t1_ = clock64(); A.dbg[role * 16 + (slot)] += t1_ - t_ph; t_ph = t1_; } } while (0)
+
 template <int MAXT, int DT, int MINB>
 __global__ void __launch_bounds__(PAIR_TEAMS * 64, MINB) factor_pair_kernel(const FactorArgs A) {
     static_assert(MAXT <= 14, "MAXT");
@@ -318,11 +322,15 @@ __global__ void __launch_bounds__(PAIR_TEAMS * 64, MINB) factor_pair_kernel(cons
             cp_async8(raw + (buf ^ 1) * RAWLD + lane, A.cand + pin + (int64_t)lane * A.ldc);
         }
         if (A.design_mode != DESIGN_SHARED) stage_design<64>(A, dsg, Xs, tl);
+        long long t_ph = (A.dbg && blockIdx.x == 0) ? clock64() : 0;
         named_sync(bar_step, 64);                                        // parameters (and the design) visible
+        CCGP_PT(0);
 
         if (prm->clamp) mma_build<DT, true>(A, Ls, Xs, ys, prm, etab, role, 2, lane);
         else mma_build<DT, false>(A, Ls, Xs, ys, prm, etab, role, 2, lane);
+        CCGP_PT(1);
         named_sync(bar_step, 64);
+        CCGP_PT(2);
 
         FactorResult res;
         res.mant_all = 1.0; res.mant_tail = 1.0; res.es_all = 0; res.es_tail = 0; res.bad = 0;
@@ -339,10 +347,13 @@ __global__ void __launch_bounds__(PAIR_TEAMS * 64, MINB) factor_pair_kernel(cons
                     st2(blk + 2 * lane, t.x, t.y);
                     __syncwarp();
                 }
+                CCGP_PT(3);
                 mma_diag(A, blk, linv, c, lane, res);
                 __threadfence_block();
                 named_arrive(bar_pub, 64);                               // L_cc and its inverse are published
+                CCGP_PT(4);
                 named_sync(bar_step, 64);                                // panel c complete
+                CCGP_PT(5);
             }
         } else {
             // ---------------- warp B: everything below the diagonal ----------------
@@ -380,7 +391,9 @@ __global__ void __launch_bounds__(PAIR_TEAMS * 64, MINB) factor_pair_kernel(cons
                     }
                 }
                 // solve against the diagonal block once A has published it
+                CCGP_PT(3);
                 named_sync(bar_pub, 64);
+                CCGP_PT(4);
                 {
                     const double2 li = ld2(linv + 2 * lane);
                     double* cb = Ls + tile_off(c, c, npad) + 2 * lane;
@@ -394,7 +407,9 @@ __global__ void __launch_bounds__(PAIR_TEAMS * 64, MINB) factor_pair_kernel(cons
 #pragma unroll
                 for (int t = 0; t < MAXT; ++t) cur[t] = nxt[t];
                 __threadfence_block();
+                CCGP_PT(5);
                 named_sync(bar_step, 64);                                // panel c complete
+                CCGP_PT(6);
             }
             // parameters of the next candidate while A reduces this one
             cp_async_wait_all();
@@ -462,6 +477,8 @@ __global__ void __launch_bounds__(PAIR_TEAMS * 64, MINB) factor_pair_kernel(cons
         }
         __threadfence_block();
         buf ^= 1;
+        CCGP_PT(7);
+        if (A.dbg && blockIdx.x == 0 && team == 0 && lane == 0 && role == 0) A.dbg[15] += 1;
     }
 }
 

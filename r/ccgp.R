@@ -115,3 +115,43 @@ Entropy <- function(D, p, theta1, theta2) entropy.batch(NULL, list(as.matrix(D))
 # [M]:869-877 (R.old.Inv is accepted for signature parity; the kernel refactors R.old itself)
 Augmented.Mixed.Entropy <- function(D.old, D.new, p, theta1, theta2, R.old.Inv = NULL)
   entropy.batch(D.old, list(as.matrix(D.new)), matrix(c(p, theta1, theta2), 1))[1, 1]
+
+# ---- lock-step Metro (SURVEY 8f rank 1) --------------------------------------------------------
+# C independent copies of the reference's Metro loop ([A]:484-539, after its laplace() step),
+# advanced together: one logpost.batch() call per iteration over the chains still running.
+# pars: list(mu = C x k matrix of chain starts, v = k x k proposal matrix, as laplace() returns it).
+# Same proposal (rmnorm(1, theta.old, sqrt(2) * v)), same acceptance rule, same Geweke stop on the
+# first column; an NA likelihood rejects the candidate instead of aborting the script.
+# R.Inv of the retained samples is recomputed on demand (one ccgp_R_rinv_batch call) instead of
+# being carried through the loop.
+Metro.multichain <- function(pars, N, samp.size, batch.size, alpha, D.train, sigma2, y, family, log.prior) {
+  mu <- as.matrix(pars$mu); C <- nrow(mu); k <- ncol(mu)
+  samp <- array(0, c(C, N, k)); beta <- matrix(0, C, N)
+  theta.old <- mu
+  l.old <- logpost.batch(D.train, theta.old, y, sigma2, family, log.prior)$val
+  kk <- rep(1L, C); pv <- rep(0, C); running <- rep(TRUE, C)
+  while (any(running)) {
+    idx <- which(running)
+    u <- runif(length(idx))
+    cand <- t(sapply(idx, function(c) rmnorm(1, as.vector(theta.old[c, ]), sqrt(2) * pars$v)))
+    l.cand <- logpost.batch(D.train, cand, y, sigma2, family, log.prior)
+    R <- l.cand$val - l.old[idx]
+    acc <- !is.na(R) & R > log(u)
+    for (j in which(acc)) {
+      c <- idx[j]
+      samp[c, kk[c], ] <- cand[j, ]; beta[c, kk[c]] <- l.cand$beta[j]
+      theta.old[c, ] <- cand[j, ]; l.old[c] <- l.cand$val[j]; kk[c] <- kk[c] + 1L
+    }
+    for (c in idx) {
+      if ((kk[c] - 1) >= samp.size && (kk[c] - 1) %% batch.size == 0) {
+        p1 <- try(min(2 * (1 - pnorm(abs(geweke.diag(mcmc(samp[c, (kk[c] - samp.size):(kk[c] - 1), 1]))$z)))), silent = TRUE)
+        pv[c] <- if (inherits(p1, "try-error") || is.na(p1)) 0 else p1
+      }
+      if (kk[c] > N || pv[c] >= alpha) running[c] <- FALSE
+    }
+  }
+  lapply(seq_len(C), function(c) {
+    rows <- (kk[c] - samp.size):(kk[c] - 1)
+    list(sample = data.frame(samp[c, rows, ]), beta = beta[c, rows])
+  })
+}
