@@ -416,3 +416,89 @@ def test_one_dimensional_families(engine, golden, tag, family, ofam):
     finally:
         orc.MATERN_NU = 5.0
         engine.set_matern_nu(5.0)
+
+
+# ---------------------------------------------------------------- every DMMA kernel family, forced
+_KERNELS = [("warp", {"CCGP_KERNEL": "1"}), ("pair", {"CCGP_KERNEL": "2"}), ("team2", {"CCGP_KERNEL": "3", "CCGP_TEAM_NW": "2"}),
+            ("team3", {"CCGP_KERNEL": "3", "CCGP_TEAM_NW": "3"}), ("team4", {"CCGP_KERNEL": "3", "CCGP_TEAM_NW": "4"}),
+            ("cta4", {"CCGP_KERNEL": "4", "CCGP_MMA_MIN_NPAD": "0"}), ("cta2", {"CCGP_KERNEL": "4", "CCGP_MMA_NW": "2", "CCGP_MMA_MIN_NPAD": "0"})]
+_KEYS = ("CCGP_KERNEL", "CCGP_TEAM_NW", "CCGP_MMA_NW", "CCGP_MMA_MIN_NPAD", "CCGP_NO_MMA")
+
+
+def _with_env(env, fn):
+    for k in _KEYS:
+        os.environ.pop(k, None)
+    os.environ.update(env)
+    try:
+        return fn()
+    finally:
+        for k in _KEYS:
+            os.environ.pop(k, None)
+
+
+@pytest.mark.parametrize("n,d,family", [(14, 2, GAUSS_ISO), (23, 9, GAUSS_ISO), (47, 3, GAUSS_ANISO_LAMBDA), (62, 2, GAUSS_ISO),
+                                        (63, 2, GAUSS_ISO_RAW2), (78, 4, GAUSS_ISO), (100, 2, GAUSS_ANISO_LAMBDA),
+                                        (102, 2, GAUSS_ISO), (110, 2, GAUSS_ANISO_LAMBDA)])
+def test_every_dmma_kernel_agrees(engine, n, d, family):
+    """The one-warp, two-warp, team and CTA tensor-path kernels and the DFMA kernel give the same likelihoods
+    (to rounding: they sum in different orders), over batches long enough that every team processes several
+    candidates (exercises the staged parameter rows), ragged n (n+2 not a multiple of 8, y' and 1' rows in
+    different tile rows), both mean modes; a few rows are checked against the oracle."""
+    rng = np.random.default_rng(7000 + n)
+    X = rng.uniform(-1, 1, (n, d))
+    y = np.cos(2 * X[:, 0]) + 0.2 * rng.normal(size=n)
+    B = 5000
+    scale = 3.0 * n ** (1.0 / d)
+    if family == GAUSS_ANISO_LAMBDA:
+        nat = np.column_stack([rng.uniform(0.1, 0.9, B)] + [scale * rng.uniform(1, 3, B) for _ in range(d)] + [rng.uniform(0.3, 2, B)])
+        of = orc.FAMILY_ANISO_LAMBDA
+    else:
+        nat = np.column_stack([rng.uniform(0.1, 0.9, B), scale * rng.uniform(1, 3, B), scale * rng.uniform(2, 6, B)])
+        of = orc.FAMILY_ISO if family == GAUSS_ISO else orc.FAMILY_ISO_RAW2
+    nat[17, 1:] *= 1e-19                                   # R = all ones exactly: singular, NA in every kernel
+    engine.set_design(X, y)
+
+    def run():
+        a = engine.nll_batch(nat, family, 1.3)
+        b = engine.nll_batch(nat, family, 1.3, mean_mode=MEAN_ZERO_PLUS_TAU2, tau=40.0)
+        return a, b, engine.last_nll_config()["variant"]
+
+    (ref, ref_t, _) = _with_env({"CCGP_NO_MMA": "1"}, run)
+    assert ref[2][17] == 1 and np.isnan(ref[0][17])
+    ok = ref[2] == 0
+    assert ok.sum() >= B - 1
+    for b in (0, 1, B - 1):
+        o = orc.loglik_reference(X, y, 1.3, of, nat[b])
+        assert rel_err(-ref[0][b], o["loglik"]) < TOL
+    seen = set()
+    for name, env in _KERNELS:
+        (got, got_t, variant) = _with_env(env, run)
+        seen.add(variant)
+        assert np.array_equal(got[2], ref[2]), name
+        assert rel_err(got[0][ok], ref[0][ok]).max() < 1e-11, (name, variant)
+        assert rel_err(got[1][ok], ref[1][ok]).max() < 1e-9, (name, variant)
+        assert rel_err(got_t[0][ok], ref_t[0][ok]).max() < 1e-11, (name, variant)
+        again = _with_env(env, run)[0]
+        assert np.array_equal(again[0][ok], got[0][ok]), name           # run-to-run bit-reproducible
+    assert len(seen) >= 5                                                # the switches really select different kernels
+
+
+def test_determinant_mode_on_every_dmma_kernel(engine, golden, designs):
+    """Subset log-dets (gather mode) and the generic ME Schur path (old + new design mode) on each kernel family."""
+    pool, par = golden["sub_pool"], golden["sub_params"]
+    D_old = designs["me_initial14"]
+    cand = designs["me_all_subdesigns"].reshape(1000, 7, 2)[:64]
+    params = [[0.5, 1.0, 4.0], [0.3, 2.0, 3.0]]
+    os.environ["CCGP_ME_GENERIC"] = "1"
+    try:
+        base_me = _with_env({"CCGP_NO_MMA": "1"}, lambda: engine.me_schur_batch(D_old, cand, params)[0])
+        for name, env in _KERNELS:
+            for m in (7, 21, 64):
+                got, st = _with_env(env, lambda: engine.subset_logdet_batch(pool, golden["sub_idx_%d" % m], GAUSS_ANISO_LAMBDA, par))
+                assert np.all(st == 0), name
+                assert np.abs(got - golden["sub_logdet_%d" % m]).max() < 1e-9, (name, m)
+            nd = _with_env(env, lambda: engine.me_schur_batch(D_old, cand, params)[0])
+            assert rel_err(nd, base_me).max() < 1e-10, name
+            assert np.array_equal(np.argmin(nd, axis=0), np.argmin(base_me, axis=0)), name
+    finally:
+        os.environ.pop("CCGP_ME_GENERIC", None)
