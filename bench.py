@@ -180,6 +180,7 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "ERROR")      # keeps NCCL's version banner off stdout (one JSON line)
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     eng = ccgp_b200.Engine(local_rank)
     stream = torch.cuda.current_stream(dev)

@@ -130,6 +130,10 @@ extern "C" int ccgp_destroy(ccgp_ctx* ctx) {
     if (ctx->ws2) cudaFree(ctx->ws2);
     if (ctx->sm_slots) cudaFree(ctx->sm_slots);
     ctx->big.release();
+    if (ctx->copy_stream) {
+        cudaStreamDestroy(ctx->copy_stream);
+        for (int i = 0; i < 2; ++i) { cudaEventDestroy(ctx->ev_h2d[i]); cudaEventDestroy(ctx->ev_kern[i]); }
+    }
     cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return CCGP_OK;
@@ -322,16 +326,48 @@ extern "C" int ccgp_nll_batch(ccgp_ctx* ctx, int family, int scale, const double
     double* d_nll = d_cand + (size_t)B * k;
     double* d_beta = d_nll + B;
     int32_t* d_status = (int32_t*)(d_beta + B);
-    if (ldc == B) {
-        CK(cudaMemcpyAsync(d_cand, cand, (size_t)B * k * 8, cudaMemcpyHostToDevice, ctx->stream));
-    } else {
-        CK(cudaMemcpy2DAsync(d_cand, (size_t)B * 8, cand, (size_t)ldc * 8, (size_t)B * 8, k, cudaMemcpyHostToDevice, ctx->stream));
+    // Chunk pipeline: the rows of chunk i+1 travel host->device (copy stream) while the kernel of chunk i
+    // runs (compute stream) and the results of chunk i-1 travel back; copies from pageable host memory block
+    // the calling thread, not the GPU.  Small batches go through in one piece.
+    int64_t nchunk = env_int("CCGP_H2D_CHUNKS", 0);
+    if (nchunk <= 0) nchunk = (B >= (1 << 16)) ? 8 : 1;
+    if (!ctx->copy_stream) {
+        CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            CK(cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&ctx->ev_kern[i], cudaEventDisableTiming));
+        }
     }
-    rc = ccgp_nll_batch_dev(ctx, family, scale, d_cand, B, B, sigma2, mean_mode, tau, d_nll, d_beta, d_status);
-    if (rc) return rc;
-    CK(cudaMemcpyAsync(out_nll, d_nll, (size_t)B * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    if (out_beta) CK(cudaMemcpyAsync(out_beta, d_beta, (size_t)B * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    if (out_status) CK(cudaMemcpyAsync(out_status, d_status, (size_t)B * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    const int64_t step = (B + nchunk - 1) / nchunk;
+    auto fetch = [&](int64_t b0, int64_t nb) -> int {       // results of rows [b0, b0+nb) -> host, after their kernel
+        CK(cudaMemcpyAsync(out_nll + b0, d_nll + b0, (size_t)nb * 8, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        if (out_beta) CK(cudaMemcpyAsync(out_beta + b0, d_beta + b0, (size_t)nb * 8, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        if (out_status) CK(cudaMemcpyAsync(out_status + b0, d_status + b0, (size_t)nb * 4, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        return 0;
+    };
+    // the copy stream must not overtake work already queued on the compute stream that still reads the workspace
+    CK(cudaEventRecord(ctx->ev_kern[0], ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_kern[0], 0));
+    int64_t prev_b0 = -1, prev_nb = 0;
+    int slot = 0;
+    for (int64_t b0 = 0; b0 < B; b0 += step, slot ^= 1) {
+        const int64_t nb = std::min(step, B - b0);
+        CK(cudaMemcpy2DAsync(d_cand + b0, (size_t)B * 8, cand + b0, (size_t)ldc * 8, (size_t)nb * 8, k, cudaMemcpyHostToDevice,
+                             ctx->copy_stream));
+        CK(cudaEventRecord(ctx->ev_h2d[slot], ctx->copy_stream));
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[slot], 0));
+        rc = ccgp_nll_batch_dev(ctx, family, scale, d_cand + b0, nb, B, sigma2, mean_mode, tau, d_nll + b0, d_beta + b0, d_status + b0);
+        if (rc) return rc;
+        CK(cudaEventRecord(ctx->ev_kern[slot], ctx->stream));
+        if (prev_b0 >= 0) {
+            CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_kern[slot ^ 1], 0));
+            if ((rc = fetch(prev_b0, prev_nb))) return rc;
+        }
+        prev_b0 = b0; prev_nb = nb;
+    }
+    CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_kern[slot ^ 1], 0));
+    if ((rc = fetch(prev_b0, prev_nb))) return rc;
+    CK(cudaStreamSynchronize(ctx->copy_stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return CCGP_OK;
 }

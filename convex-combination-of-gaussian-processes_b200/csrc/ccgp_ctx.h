@@ -20,6 +20,8 @@ struct ccgp_ctx {
     int max_smem_optin = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t own_stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // host<->device copies of the chunk-pipelined host-pointer entry points
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_kern[2] = {nullptr, nullptr};
     int n = 0, d = 0;
     double* d_X = nullptr;
     double* d_y = nullptr;
