@@ -156,6 +156,54 @@ __device__ __forceinline__ void mma_build(const FactorArgs& A, double* Ls, const
     }
 }
 
+// ---- one raw tile (r, c) of A = [R; y'; 1'] straight into this lane's fragment slot ---------------
+// Same arithmetic as mma_build, for kernels that never store the unfactored matrix (fused build).
+template <int DT, bool CLAMP>
+__device__ __forceinline__ double2 mma_raw_tile(const FactorArgs& A, const double* Xs, const double* ys, const Prm* prm,
+                                                const double* T, int r, int c, int lane) {
+    const int n = A.lay.n, naug = A.lay.naug, npx = A.lay.npx, d = A.d;
+    const int g = lane >> 2, m = lane & 3;
+    const int j0 = 8 * c + 2 * m, j1 = j0 + 1;
+    const int jc0 = min(j0, n - 1), jc1 = min(j1, n - 1);
+    const int i = 8 * r + g;
+    const int ic = min(i, n - 1);
+    double s0 = 0.0, s1 = 0.0;
+    if (DT > 0) {
+#pragma unroll
+        for (int k = 0; k < DT; ++k) {
+            const double xi = Xs[k * npx + ic], wk = prm->wts[k];
+            const double d0 = xi - Xs[k * npx + jc0], d1 = xi - Xs[k * npx + jc1];
+            s0 = fma(wk * d0, d0, s0);
+            s1 = fma(wk * d1, d1, s1);
+        }
+    } else {
+        for (int k = 0; k < d; ++k) {
+            const double xi = Xs[k * npx + ic], wk = prm->wts[k];
+            const double d0 = xi - Xs[k * npx + jc0], d1 = xi - Xs[k * npx + jc1];
+            s0 = fma(wk * d0, d0, s0);
+            s1 = fma(wk * d1, d1, s1);
+        }
+    }
+    const double rho = prm->rho, a = prm->a, b = prm->b;
+    double v0 = fma(b, dexp_neg_tab_dev<CLAMP>(rho * s0, T), a * dexp_neg_tab_dev<CLAMP>(s0, T));
+    double v1 = fma(b, dexp_neg_tab_dev<CLAMP>(rho * s1, T), a * dexp_neg_tab_dev<CLAMP>(s1, T));
+    if (r == c || 8 * r + 7 >= n) {                       // warp-uniform: diagonal tile or rows beyond the design
+        if (i < n) {
+            if (j0 >= i) v0 = (j0 == i) ? 1.0 : 0.0;
+            if (j1 >= i) v1 = (j1 == i) ? 1.0 : 0.0;
+        } else if (naug && i == n) {
+            v0 = (j0 < n) ? ys[j0] : 0.0;
+            v1 = (j1 < n) ? ys[j1] : 0.0;
+        } else if (naug && i == n + 1) {
+            v0 = (j0 < n) ? 1.0 : 0.0;
+            v1 = (j1 < n) ? 1.0 : 0.0;
+        } else {
+            v0 = 0.0; v1 = 0.0;
+        }
+    }
+    return make_double2(v0, v1);
+}
+
 // ---- 8x8 diagonal tile, one warp: Cholesky + inverse of the factor -------------------------------
 // Every lane holds the whole lower triangle (as diag_block of factor_engine.cuh); lane j (mod 8)
 // additionally builds column j of inv(L) by forward substitution, interleaved with the factor

@@ -7,7 +7,7 @@
 // ---- DMMA variants (factor_mma.cuh): NW warps per candidate, MAXT tiles per update warp ----
 struct MmaVariant { int nw, maxt; factor_fn fn_d0, fn_d2; };
 #define M(NWv, MT) {NWv, MT, factor_mma_kernel<NWv, MT, 0>, factor_mma_kernel<NWv, MT, 2>},
-static const MmaVariant g_mma_variants[] = {M(4, 2) M(4, 4) M(4, 6) M(4, 9) M(3, 3) M(3, 6) M(3, 9) M(2, 6) M(2, 12)};
+static const MmaVariant g_mma_variants[] = {M(4, 6) M(4, 9) M(2, 12)};
 #undef M
 static const int g_num_mma_variants = sizeof(g_mma_variants) / sizeof(g_mma_variants[0]);
 
@@ -18,13 +18,15 @@ static const WarpVariant g_warp_variants[] = {WV(4, 3) WV(8, 2) WV(14, 1)};
 #undef WV
 
 // ---- team kernel (factor_team.cuh): NW warps per candidate on one sub-partition; nrmax = most tile rows ----
-struct TeamVariant { int nw, nrmax, maxt; factor_fn fn_d0, fn_d2; };
-#define TV(NWv, NRM, MT, MB) {NWv, NRM, MT, factor_team_kernel<NWv, MT, 0, MB>, factor_team_kernel<NWv, MT, 2, MB>},
-static const TeamVariant g_team_variants[] = {
-    TV(2, 5, 4, 1) TV(2, 9, 8, 1) TV(2, 14, 13, 1)
-    TV(3, 5, 2, 1) TV(3, 9, 4, 1) TV(3, 14, 7, 1)
-    TV(4, 5, 2, 1) TV(4, 9, 3, 1) TV(4, 14, 5, 1)};
+struct TeamVariant { int nw, nrmax, maxt; factor_fn fn_d0, fn_d2, fu_d0, fu_d2; };
+#define TV(NWv, NRM, MT, MB) {NWv, NRM, MT, factor_team_kernel<NWv, MT, 0, MB, false>, factor_team_kernel<NWv, MT, 2, MB, false>, \
+                              nullptr, nullptr},
+// the fused-build experiment (CCGP_TEAM_FUSED=1) is instantiated for the production team size only
+#define TVF(NWv, NRM, MT, MB) {NWv, NRM, MT, factor_team_kernel<NWv, MT, 0, MB, false>, factor_team_kernel<NWv, MT, 2, MB, false>, \
+                               factor_team_kernel<NWv, MT, 0, MB, true>, factor_team_kernel<NWv, MT, 2, MB, true>},
+static const TeamVariant g_team_variants[] = {TV(2, 14, 13, 1) TVF(3, 14, 7, 1) TV(4, 14, 5, 1)};
 #undef TV
+#undef TVF
 
 static int launch_factor_team(ccgp_ctx* ctx, FactorArgs& A, int* launched) {
     *launched = 0;
@@ -39,7 +41,8 @@ static int launch_factor_team(ccgp_ctx* ctx, FactorArgs& A, int* launched) {
     const size_t smem = tsm * TEAMS_PER_CTA + TEAM_CTA_EXTRA;
     if (smem > (size_t)ctx->max_smem_optin) return 0;
     const int threads = TEAMS_PER_CTA * var->nw * 32;
-    factor_fn fn = (A.d == 2) ? var->fn_d2 : var->fn_d0;
+    const bool fused = env_int("CCGP_TEAM_FUSED", 0) != 0 && var->fu_d0 != nullptr;   // measured slower (14.6 vs 16.8 M/s at n=100)
+    factor_fn fn = fused ? ((A.d == 2) ? var->fu_d2 : var->fu_d0) : ((A.d == 2) ? var->fn_d2 : var->fn_d0);
     CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int nb = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, threads, smem));
@@ -54,43 +57,7 @@ static int launch_factor_team(ccgp_ctx* ctx, FactorArgs& A, int* launched) {
     fn<<<(unsigned)grid, threads, smem, ctx->stream>>>(A);
     CK(cudaGetLastError());
     ctx->launches++;
-    ctx->last_team = var->nw * 32; ctx->last_smem = (int)smem; ctx->last_ctas = nb; ctx->last_variant = 400 + var->nw * 10;
-    *launched = 1;
-    return 0;
-}
-
-struct PairVariant { int maxt, minb; factor_fn fn_d0, fn_d2; };
-#define PV(MT, MB) {MT, MB, factor_pair_kernel<MT, 0, MB>, factor_pair_kernel<MT, 2, MB>},
-static const PairVariant g_pair_variants[] = {PV(4, 2) PV(8, 1) PV(14, 1)};
-#undef PV
-
-static int launch_factor_pair(ccgp_ctx* ctx, FactorArgs& A, int* launched) {
-    *launched = 0;
-    const Layout& l = A.lay;
-    const int NR = l.npad / 8;
-    const PairVariant* var = nullptr;
-    for (const PairVariant& v : g_pair_variants)
-        if (NR <= v.maxt) { var = &v; break; }
-    if (!var) return 0;
-    const size_t team_smem = pair_team_smem_bytes(l, A.d);
-    const size_t smem = team_smem * PAIR_TEAMS + WARP_CTA_EXTRA;
-    if (smem > (size_t)ctx->max_smem_optin) return 0;
-    factor_fn fn = (A.d == 2) ? var->fn_d2 : var->fn_d0;
-    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int nb = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, PAIR_TEAMS * 64, smem));
-    if (nb < 1) return 0;
-    { int cap = env_int("CCGP_CTAS_PER_SM", 0); if (cap > 0 && cap < nb) nb = cap; }
-    int64_t grid = (int64_t)nb * ctx->num_sm;
-    if (grid * PAIR_TEAMS > A.W) grid = (A.W + PAIR_TEAMS - 1) / PAIR_TEAMS;
-    if (grid < 1) { *launched = 1; return 0; }
-    A.team_smem_bytes = (int64_t)team_smem;
-    A.dbg = ctx->dbg;
-    A.nparams = (A.family == FAM_ANISO) ? A.d + 2 : 3;
-    fn<<<(unsigned)grid, PAIR_TEAMS * 64, smem, ctx->stream>>>(A);
-    CK(cudaGetLastError());
-    ctx->launches++;
-    ctx->last_team = 64; ctx->last_smem = (int)smem; ctx->last_ctas = nb; ctx->last_variant = 300 + var->maxt;
+    ctx->last_team = var->nw * 32; ctx->last_smem = (int)smem; ctx->last_ctas = nb; ctx->last_variant = 400 + var->nw * 10 + (fused ? 1 : 0);
     *launched = 1;
     return 0;
 }
@@ -136,13 +103,9 @@ int launch_factor_mma(ccgp_ctx* ctx, FactorArgs& A, int* launched) {
     const Layout& l = A.lay;
     if (A.family >= FAM_MATERN1D || env_int("CCGP_NO_MMA", 0)) return 0;
     const int NR = l.npad / 8;
-    const int kern = env_int("CCGP_KERNEL", 0);      // 0 auto, 1 warp, 2 pair, 3 team, 4 cta
+    const int kern = env_int("CCGP_KERNEL", 0);      // 0 auto, 1 warp, 3 team, 4 cta
     if ((kern == 0 && NR <= 10) || kern == 1) {
         RC(launch_factor_warp(ctx, A, launched));
-        if (*launched) return 0;
-    }
-    if (kern == 2) {
-        RC(launch_factor_pair(ctx, A, launched));
         if (*launched) return 0;
     }
     if ((kern == 0 && NR <= 14) || kern == 3) {

@@ -98,11 +98,25 @@ __device__ __forceinline__ void team_solve_nt(int nt, const double2 (&acc)[MAXT]
     }
 }
 
-// phase timing (debug, tools/phase_timing_pair.py): team 0 of block 0; warp A slots 0.., warp B_0 slots 16..
+// acc[i] = v for a runtime i without dynamic register indexing (a select chain: cheap next to the
+// ~200-instruction tile computation it follows, and it keeps that computation a real loop body)
+template <int MAXT>
+__device__ __forceinline__ void put_tile(double2 (&acc)[MAXT], int i, double2 v) {
+#pragma unroll
+    for (int q = 0; q < MAXT; ++q) {
+        acc[q].x = (q == i) ? v.x : acc[q].x;
+        acc[q].y = (q == i) ? v.y : acc[q].y;
+    }
+}
+
+// phase timing (debug, tools/phase_timing_pair.py, CCGP_KERNEL=3 CCGP_TEAM_NW=2): team 0 of block 0; warp A slots 0.., warp B_0 slots 16..
 #define CCGP_TT(slot) do { if (A.dbg && blockIdx.x == 0 && team == 0 && lane == 0 && role < 2) { \
         long long t1_ = clock64(); A.dbg[role * 16 + (slot)] += t1_ - t_ph; t_ph = t1_; } } while (0)
 
-template <int NW, int MAXT, int DT, int MINB>
+// FUSED: the unfactored matrix is never stored -- each B warp computes the raw tiles of column c+1 (2 table
+// exponentials per entry) straight into its lookahead accumulators during step c, so the FP64-issue-heavy
+// build fills the slots the serial chain and the DMMA queue leave idle instead of running as a phase of its own.
+template <int NW, int MAXT, int DT, int MINB, bool FUSED>
 __global__ void __launch_bounds__(TEAMS_PER_CTA * NW * 32, MINB) factor_team_kernel(const FactorArgs A) {
     constexpr int NU = NW - 1;
     constexpr int TT = NW * 32;                                           // threads of a team
@@ -155,10 +169,19 @@ __global__ void __launch_bounds__(TEAMS_PER_CTA * NW * 32, MINB) factor_team_ker
         named_sync(bar_step, TT);                                        // parameters (and the design) visible
         CCGP_TT(0);
 
-        if (prm->clamp) mma_build<DT, true>(A, Ls, Xs, ys, prm, etab, role, NW, lane);
-        else mma_build<DT, false>(A, Ls, Xs, ys, prm, etab, role, NW, lane);
+        const bool clampx = prm->clamp != 0;
+#define CCGP_RAW(r_, c_) (clampx ? mma_raw_tile<DT, true>(A, Xs, ys, prm, etab, (r_), (c_), lane) \
+                                 : mma_raw_tile<DT, false>(A, Xs, ys, prm, etab, (r_), (c_), lane))
+        if (!FUSED) {
+            if (clampx) mma_build<DT, true>(A, Ls, Xs, ys, prm, etab, role, NW, lane);
+            else mma_build<DT, false>(A, Ls, Xs, ys, prm, etab, role, NW, lane);
+        } else if (role == 1) {                                          // B_0: the first diagonal tile
+            const double2 t00 = CCGP_RAW(0, 0);
+            st2(Ls + 2 * lane, t00.x, t00.y);
+        }
         CCGP_TT(1);
-        named_sync(bar_step, TT);
+        if (!FUSED) named_sync(bar_step, TT);
+        else if (role <= 1) named_sync(1 + 2 * TEAMS_PER_CTA + team, 64);    // only A waits for B_0's tile (0,0)
         CCGP_TT(2);
 
         FactorResult res;
@@ -192,7 +215,11 @@ __global__ void __launch_bounds__(TEAMS_PER_CTA * NW * 32, MINB) factor_team_ker
             {
                 const int own0 = (NR - 2 - u + NU) / NU;                 // own tiles of column 0
 #pragma unroll
-                for (int i = 0; i < MAXT; ++i) cur[i] = (i < own0) ? ld2(Ll + 64 * (1 + u + NU * i)) : make_double2(0.0, 0.0);
+                for (int i = 0; i < MAXT; ++i) cur[i] = (!FUSED && i < own0) ? ld2(Ll + 64 * (1 + u + NU * i)) : make_double2(0.0, 0.0);
+                if (FUSED) {
+#pragma unroll 1
+                    for (int i = 0; i < own0; ++i) put_tile<MAXT>(cur, i, CCGP_RAW(1 + u + NU * i, 0));
+                }
             }
             for (int c = 0; c < NJ; ++c) {
                 const int nt = NR - c;                                   // tiles (c+t, c), t < nt; t = 0 is A's
@@ -207,7 +234,15 @@ __global__ void __launch_bounds__(TEAMS_PER_CTA * NW * 32, MINB) factor_team_ker
                     const int own1 = (nt - 3 - u + NU) / NU;
                     const double* nb = Ll + tile_off(c + 1, c + 1, npad);
 #pragma unroll
-                    for (int i = 0; i < MAXT; ++i) nxt[i] = (i < own1) ? ld2(nb + 64 * (1 + u + NU * i)) : make_double2(0.0, 0.0);
+                    for (int i = 0; i < MAXT; ++i) nxt[i] = (!FUSED && i < own1) ? ld2(nb + 64 * (1 + u + NU * i)) : make_double2(0.0, 0.0);
+                    if (FUSED) {
+#pragma unroll 1
+                        for (int i = 0; i < own1; ++i) put_tile<MAXT>(nxt, i, CCGP_RAW(c + 2 + u + NU * i, c + 1));
+                    }
+                    if (FUSED && u == 0 && c == 0) {                     // raw diagonal tile (1,1): no panel to apply yet
+                        const double2 t11 = CCGP_RAW(1, 1);
+                        st2(Ls + tile_off(1, 1, npad) + 2 * lane, t11.x, t11.y);
+                    }
                     if (c > 0) {
                         const double* bp = Ll + 64 * (c + 1);            // tile (c+1, 0)
                         const int inc = 8 * npad - 64;
@@ -215,7 +250,7 @@ __global__ void __launch_bounds__(TEAMS_PER_CTA * NW * 32, MINB) factor_team_ker
                             dg = make_double2(0.0, 0.0); dg2 = make_double2(0.0, 0.0);
                             team_panels_nt<0, MAXT, NU, true>(own1, nxt, dg, dg2, bp, bp + 64 * (1 + u), inc, c);
                             double* dp = Ls + tile_off(c + 1, c + 1, npad) + 2 * lane;
-                            const double2 t0 = ld2(dp);
+                            const double2 t0 = FUSED ? CCGP_RAW(c + 1, c + 1) : ld2(dp);
                             st2(dp, t0.x + (dg.x + dg2.x), t0.y + (dg.y + dg2.y));
                         } else if (own1 > 0) {
                             team_panels_nt<1, MAXT, NU, false>(own1, nxt, dg, dg2, bp, bp + 64 * (1 + u), inc, c);
@@ -306,5 +341,7 @@ __global__ void __launch_bounds__(TEAMS_PER_CTA * NW * 32, MINB) factor_team_ker
         if (A.dbg && blockIdx.x == 0 && team == 0 && lane == 0 && role == 0) A.dbg[15] += 1;
     }
 }
+
+#undef CCGP_RAW
 
 }  // namespace ccgp

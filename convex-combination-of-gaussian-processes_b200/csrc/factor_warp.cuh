@@ -252,234 +252,4 @@ __global__ void __launch_bounds__(WARP_TEAMS * 32, MINB) factor_warp_kernel(cons
 }
 
 
-// =================================================================================================
-// factor_pair_kernel: TWO warps per candidate, both on the same SM sub-partition.
-// A CTA has 8 warps = 4 teams; team t is warps t and t+4, which the hardware places on
-// sub-partition t, so each candidate still owns one FP64 pipe -- but now the serial diagonal
-// chain (warp A) and the tensor-path updates (warp B) of the SAME candidate interleave on it:
-// the chain's latency gaps are filled by B's DMMAs instead of idling (a lone warp reached ~40 %
-// issue utilisation, profiles/).  Per step c:
-//   A: tile(c,c) -= L(c,c-1) L(c,c-1)';  8x8 Cholesky + inverse;  publish (named barrier)
-//   B: tiles (c+t, c), t >= 1, live in registers: last panel c-1 in;  LOOKAHEAD: tiles of column
-//      c+1 through panel c-1 (its diagonal tile goes back to shared memory for A);  wait for A;
-//      solve against inv(L_cc) (2 DMMA per tile), store;  team barrier.
-// While A reduces the scalars of candidate w, B already transforms the parameters of w+1.
-constexpr int PAIR_TEAMS = 4;
-inline size_t pair_team_smem_bytes(const Layout& l, int d) {
-    size_t dbl = (size_t)l.total + (size_t)d * l.npx + l.npx + 64 + 2 * (MAXD + 2);
-    return (dbl * 8 + 2 * sizeof(Prm) + 15) / 16 * 16;
-}
-
-// phase timing (debug, tools/phase_timing_pair.py): team 0 of block 0; warp A slots 0.., warp B slots 16..
-#define CCGP_PT(slot) do { if (A.dbg && blockIdx.x == 0 && team == 0 && lane == 0) { \
-        long long t1_ = clock64(); A.dbg[role * 16 + (slot)] += t1_ - t_ph; t_ph = t1_; } } while (0)
-
-template <int MAXT, int DT, int MINB>
-__global__ void __launch_bounds__(PAIR_TEAMS * 64, MINB) factor_pair_kernel(const FactorArgs A) {
-    static_assert(MAXT <= 14, "MAXT");
-    constexpr int RAWLD = MAXD + 2;
-    extern __shared__ __align__(16) double smem_all[];
-    const Layout& lay = A.lay;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int team = wid & (PAIR_TEAMS - 1), role = wid / PAIR_TEAMS;     // role 0: diagonal warp A, 1: update warp B
-    double* etab = smem_all;
-    double* Ls = smem_all + 128 + (size_t)team * (A.team_smem_bytes / 8);
-    double* Xs = Ls + lay.total;
-    double* ys = Xs + A.d * lay.npx;
-    double* linv = ys + lay.npx;
-    double* raw = linv + 64;
-    Prm* prm2 = reinterpret_cast<Prm*>(raw + 2 * RAWLD);                  // two parameter blocks (current / next)
-    const int n = lay.n, npad = lay.npad, NJ = lay.NJ, NR = npad >> 3;
-    const int bar_pub = 1 + team, bar_step = 1 + PAIR_TEAMS + team;       // named barriers of this team
-
-    for (int e = threadIdx.x; e < 128; e += PAIR_TEAMS * 64) etab[e] = CCGP_EXP2_TAB[e];
-    const int tl = role * 32 + lane;                                     // thread index within the team
-    if (A.design_mode == DESIGN_SHARED) {
-        for (int e = tl; e < n * A.d; e += 64) {
-            int k = e / n, i = e - k * n;
-            Xs[k * lay.npx + i] = A.X[e];
-        }
-        if (lay.naug) for (int i = tl; i < n; i += 64) ys[i] = A.y[i];
-    }
-    const int64_t w0 = (int64_t)blockIdx.x * PAIR_TEAMS + team, wstride = (int64_t)gridDim.x * PAIR_TEAMS;
-    const int nprm = A.nparams;
-    if (role == 1 && lane < nprm && w0 < A.W) {
-        const int64_t pi0 = (A.n_params == 1) ? 0 : w0 / A.n_designs;
-        cp_async8(raw + lane, A.cand + pi0 + (int64_t)lane * A.ldc);
-    }
-    cp_async_wait_all();
-    __syncthreads();
-    int buf = 0;
-    if (role == 1 && lane == 0 && w0 < A.W) load_params_from(A, raw, 1, prm2);
-    const double* Ll = Ls + 2 * lane;
-
-    for (int64_t w = w0; w < A.W; w += wstride) {
-        const int64_t dsg = w % A.n_designs;
-        const Prm* prm = prm2 + buf;
-        const int64_t wn = w + wstride;
-        if (role == 1 && lane < nprm && wn < A.W) {                       // stage the next parameter row
-            const int64_t pin = (A.n_params == 1) ? 0 : wn / A.n_designs;
-            cp_async8(raw + (buf ^ 1) * RAWLD + lane, A.cand + pin + (int64_t)lane * A.ldc);
-        }
-        if (A.design_mode != DESIGN_SHARED) stage_design<64>(A, dsg, Xs, tl);
-        long long t_ph = (A.dbg && blockIdx.x == 0) ? clock64() : 0;
-        named_sync(bar_step, 64);                                        // parameters (and the design) visible
-        CCGP_PT(0);
-
-        if (prm->clamp) mma_build<DT, true>(A, Ls, Xs, ys, prm, etab, role, 2, lane);
-        else mma_build<DT, false>(A, Ls, Xs, ys, prm, etab, role, 2, lane);
-        CCGP_PT(1);
-        named_sync(bar_step, 64);
-        CCGP_PT(2);
-
-        FactorResult res;
-        res.mant_all = 1.0; res.mant_tail = 1.0; res.es_all = 0; res.es_tail = 0; res.bad = 0;
-
-        if (role == 0) {
-            // ---------------- warp A: diagonal tiles ----------------
-            for (int c = 0; c < NJ; ++c) {
-                double* blk = Ls + tile_off(c, c, npad);
-                if (c > 0) {
-                    double2 t = ld2(blk + 2 * lane);
-                    const double2 p = ld2(Ls + tile_off(c, c - 1, npad) + 2 * lane);
-                    mma884(t.x, t.y, p.x, negd(p.x));
-                    mma884(t.x, t.y, p.y, negd(p.y));
-                    st2(blk + 2 * lane, t.x, t.y);
-                    __syncwarp();
-                }
-                CCGP_PT(3);
-                mma_diag(A, blk, linv, c, lane, res);
-                __threadfence_block();
-                named_arrive(bar_pub, 64);                               // L_cc and its inverse are published
-                CCGP_PT(4);
-                named_sync(bar_step, 64);                                // panel c complete
-                CCGP_PT(5);
-            }
-        } else {
-            // ---------------- warp B: everything below the diagonal ----------------
-            double2 cur[MAXT], nxt[MAXT];
-#pragma unroll
-            for (int t = 0; t < MAXT; ++t) cur[t] = (t >= 1 && t < NR) ? ld2(Ll + 64 * t) : make_double2(0.0, 0.0);
-            for (int c = 0; c < NJ; ++c) {
-                const int nt = NR - c;                                   // tiles (c+t, c), t < nt (t = 0: A's)
-                // last panel into the column
-                if (c > 0 && nt > 1) {
-                    const double* ap = Ll + tile_off(c, c - 1, npad);
-                    switch (nt) {
-#define CCGP_F(NTv) case NTv: if constexpr (NTv <= MAXT && NTv >= 2) warp_panels<NTv, MAXT, true>(cur, ap, 0, 1); break;
-                        CCGP_NT_CASES(CCGP_F)
-#undef CCGP_F
-                        default: break;
-                    }
-                }
-                // lookahead: column c+1 through panel c-1; its diagonal tile returns to shared memory
-                if (c + 1 < NJ) {
-                    const int nt1 = nt - 1;
-                    double* nb = Ls + tile_off(c + 1, c + 1, npad) + 2 * lane;
-#pragma unroll
-                    for (int t = 0; t < MAXT; ++t) nxt[t] = (t < nt1) ? ld2(nb + 64 * t) : make_double2(0.0, 0.0);
-                    if (c > 0) {
-                        const double* ap = Ll + 64 * (c + 1);            // tile (c+1, 0)
-                        const int inc = 8 * npad - 64;
-                        switch (nt1) {
-#define CCGP_F(NTv) case NTv: if constexpr (NTv <= MAXT) warp_panels<NTv, MAXT>(nxt, ap, inc, c); break;
-                            CCGP_NT_CASES(CCGP_F)
-#undef CCGP_F
-                            default: break;
-                        }
-                        st2(nb, nxt[0].x, nxt[0].y);
-                    }
-                }
-                // solve against the diagonal block once A has published it
-                CCGP_PT(3);
-                named_sync(bar_pub, 64);
-                CCGP_PT(4);
-                {
-                    const double2 li = ld2(linv + 2 * lane);
-                    double* cb = Ls + tile_off(c, c, npad) + 2 * lane;
-                    switch (nt) {
-#define CCGP_F(NTv) case NTv: if constexpr (NTv <= MAXT) warp_solve<NTv, MAXT>(cur, li, cb); break;
-                        CCGP_NT_CASES(CCGP_F)
-#undef CCGP_F
-                        default: break;
-                    }
-                }
-#pragma unroll
-                for (int t = 0; t < MAXT; ++t) cur[t] = nxt[t];
-                __threadfence_block();
-                CCGP_PT(5);
-                named_sync(bar_step, 64);                                // panel c complete
-                CCGP_PT(6);
-            }
-            // parameters of the next candidate while A reduces this one
-            cp_async_wait_all();
-            __syncwarp();
-            if (lane == 0 && wn < A.W) load_params_from(A, raw + (buf ^ 1) * RAWLD, 1, prm2 + (buf ^ 1));
-        }
-
-        // ---------------- scalars (warp A) ----------------
-        if (role == 0) {
-            res.bad = __any_sync(0xffffffffu, res.bad) ? 1 : 0;
-            double ma = 1.0, mt = 1.0;
-            int ea = 0, et = 0;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const double m1 = __shfl_sync(0xffffffffu, res.mant_all, 8 + k);
-                const double m2 = __shfl_sync(0xffffffffu, res.mant_tail, 8 + k);
-                const int e1 = __shfl_sync(0xffffffffu, res.es_all, 8 + k);
-                const int e2 = __shfl_sync(0xffffffffu, res.es_tail, 8 + k);
-                prod_accum(ma, ea, m1); ea += e1;
-                prod_accum(mt, et, m2); et += e2;
-            }
-            res.mant_all = ma; res.es_all = ea; res.mant_tail = mt; res.es_tail = et;
-            if (A.out_mode == OUT_NLL) {
-                double s11 = 0.0, s1y = 0.0;
-                for (int k = lane; k < n; k += 32) {
-                    const int off = elem_off_rm(n, k, npad);
-                    const double zy = Ls[off], z1 = Ls[off + 8];
-                    s11 = fma(z1, z1, s11);
-                    s1y = fma(z1, zy, s1y);
-                }
-                team_sum2<32>(s11, s1y, nullptr);
-                const double beta = s1y / s11;
-                double qr = 0.0, dummy = 0.0;
-                for (int k = lane; k < n; k += 32) {
-                    const int off = elem_off_rm(n, k, npad);
-                    const double rz = fma(-beta, Ls[off + 8], Ls[off]);
-                    qr = fma(rz, rz, qr);
-                }
-                team_sum2<32>(qr, dummy, nullptr);
-                if (lane == 0) {
-                    const double cc = prm->c;
-                    const double logdet = log(res.mant_all) + res.es_all * LN2;
-                    double nll;
-                    if (A.mean_mode == 0) {
-                        nll = 0.5 * (qr / cc + n * LOG2PI + n * log(cc) + logdet);
-                    } else {
-                        const double gg = 1.0 + A.tau * A.tau * s11 / cc;
-                        const double quad = qr / cc + s1y * s1y / (cc * s11 * gg);
-                        nll = 0.5 * (quad + n * LOG2PI + n * log(cc) + logdet + log(gg));
-                    }
-                    const bool bad = res.bad || !(nll == nll);
-                    const double nanv = __longlong_as_double(0x7ff8000000000000LL);
-                    A.out0[w] = bad ? nanv : nll;
-                    if (A.out1) A.out1[w] = bad ? nanv : beta;
-                    if (A.status) A.status[w] = bad ? 1 : 0;
-                }
-            } else if (lane == 0) {
-                const double nanv = __longlong_as_double(0x7ff8000000000000LL);
-                const bool bad = res.bad != 0;
-                if (A.out0) A.out0[w] = bad ? nanv : log(res.mant_all) + res.es_all * LN2;
-                if (A.out1) A.out1[w] = bad ? nanv : log(res.mant_tail) + res.es_tail * LN2;
-                if (A.out2) A.out2[w] = bad ? nanv : -scalbn(res.mant_tail, res.es_tail);
-                if (A.status) A.status[w] = bad ? 1 : 0;
-            }
-        }
-        __threadfence_block();
-        buf ^= 1;
-        CCGP_PT(7);
-        if (A.dbg && blockIdx.x == 0 && team == 0 && lane == 0 && role == 0) A.dbg[15] += 1;
-    }
-}
-
 }  // namespace ccgp

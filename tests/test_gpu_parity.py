@@ -419,10 +419,10 @@ def test_one_dimensional_families(engine, golden, tag, family, ofam):
 
 
 # ---------------------------------------------------------------- every DMMA kernel family, forced
-_KERNELS = [("warp", {"CCGP_KERNEL": "1"}), ("pair", {"CCGP_KERNEL": "2"}), ("team2", {"CCGP_KERNEL": "3", "CCGP_TEAM_NW": "2"}),
+_KERNELS = [("warp", {"CCGP_KERNEL": "1"}), ("team3f", {"CCGP_KERNEL": "3", "CCGP_TEAM_NW": "3", "CCGP_TEAM_FUSED": "1"}), ("team2", {"CCGP_KERNEL": "3", "CCGP_TEAM_NW": "2"}),
             ("team3", {"CCGP_KERNEL": "3", "CCGP_TEAM_NW": "3"}), ("team4", {"CCGP_KERNEL": "3", "CCGP_TEAM_NW": "4"}),
             ("cta4", {"CCGP_KERNEL": "4", "CCGP_MMA_MIN_NPAD": "0"}), ("cta2", {"CCGP_KERNEL": "4", "CCGP_MMA_NW": "2", "CCGP_MMA_MIN_NPAD": "0"})]
-_KEYS = ("CCGP_KERNEL", "CCGP_TEAM_NW", "CCGP_MMA_NW", "CCGP_MMA_MIN_NPAD", "CCGP_NO_MMA")
+_KEYS = ("CCGP_KERNEL", "CCGP_TEAM_NW", "CCGP_TEAM_FUSED", "CCGP_MMA_NW", "CCGP_MMA_MIN_NPAD", "CCGP_NO_MMA")
 
 
 def _with_env(env, fn):
@@ -440,7 +440,7 @@ def _with_env(env, fn):
                                         (63, 2, GAUSS_ISO_RAW2), (78, 4, GAUSS_ISO), (100, 2, GAUSS_ANISO_LAMBDA),
                                         (102, 2, GAUSS_ISO), (110, 2, GAUSS_ANISO_LAMBDA)])
 def test_every_dmma_kernel_agrees(engine, n, d, family):
-    """The one-warp, two-warp, team and CTA tensor-path kernels and the DFMA kernel give the same likelihoods
+    """The one-warp, team (fused and unfused build) and CTA tensor-path kernels and the DFMA kernel give the same likelihoods
     (to rounding: they sum in different orders), over batches long enough that every team processes several
     candidates (exercises the staged parameter rows), ragged n (n+2 not a multiple of 8, y' and 1' rows in
     different tile rows), both mean modes; a few rows are checked against the oracle."""

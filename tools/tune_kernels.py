@@ -15,8 +15,8 @@ dev = torch.device("cuda", 0)
 eng = ccgp_b200.Engine(0)
 stream = torch.cuda.current_stream(dev)
 eng.set_stream(stream.cuda_stream)
-KEYS = ("CCGP_MMA_NW", "CCGP_NO_MMA", "CCGP_TEAM_NW", "CCGP_KERNEL", "CCGP_VARIANT")
-configs = [("auto", {}), ("team nw4", {"CCGP_KERNEL": "3", "CCGP_TEAM_NW": "4"}), ("team nw3", {"CCGP_KERNEL": "3", "CCGP_TEAM_NW": "3"}),
+KEYS = ("CCGP_MMA_NW", "CCGP_NO_MMA", "CCGP_TEAM_NW", "CCGP_TEAM_FUSED", "CCGP_KERNEL", "CCGP_VARIANT")
+configs = [("auto", {}), ("team nw4", {"CCGP_KERNEL": "3", "CCGP_TEAM_NW": "4"}), ("team nw3", {"CCGP_KERNEL": "3", "CCGP_TEAM_NW": "3"}), ("team nw3 fused", {"CCGP_KERNEL": "3", "CCGP_TEAM_NW": "3", "CCGP_TEAM_FUSED": "1"}),
            ("team nw2", {"CCGP_KERNEL": "3", "CCGP_TEAM_NW": "2"}), ("warp", {"CCGP_KERNEL": "1"}),
            ("cta nw4", {"CCGP_KERNEL": "4"}), ("cta nw2", {"CCGP_KERNEL": "4", "CCGP_MMA_NW": "2"}),
            ("dfma default", {"CCGP_NO_MMA": "1"}), ("dfma v0 (1 warp)", {"CCGP_NO_MMA": "1", "CCGP_VARIANT": "0"})]
