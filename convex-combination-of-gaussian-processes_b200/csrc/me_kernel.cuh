@@ -37,14 +37,15 @@ inline bool me_fast_supported(int n_old, int n_new, int d) {
     return n_new >= 1 && n_new <= 8 && n_old >= 1 && n_old <= 32 && d >= 1 && d <= 4;
 }
 
-template <int NOLD>
+// NOLD: rows of the old design the kernel is unrolled for; DM: coordinates it is unrolled for (d <= DM)
+template <int NOLD, int DM>
 __global__ void __launch_bounds__(128) me_schur_kernel(const MeArgs M) {
-    constexpr int DM = 4;
     __shared__ double Lo[NOLD * NOLD];        // L_old, row-major Lo[j*NOLD + k], k <= j
     __shared__ double rio[NOLD];              // 1 / L_old(j,j)
     __shared__ double Xo[DM * NOLD];          // D_old, Xo[k*NOLD + j]
     __shared__ double abuf[4][32][NOLD + 1];  // per warp: the solved cross rows (padded against conflicts)
     __shared__ double prm[4];                 // a, b, theta1, theta2
+    __shared__ double etab[128];              // 2^(j/128): table-driven exp (ccgp_math.h)
     __shared__ int s_bad;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_old = M.n_old, n_new = M.n_new, d = M.d;
@@ -55,6 +56,7 @@ __global__ void __launch_bounds__(128) me_schur_kernel(const MeArgs M) {
         int k = e / NOLD, j = e - k * NOLD;
         Xo[e] = (k < d && j < n_old) ? M.D_old[k * n_old + j] : 0.0;
     }
+    etab[tid] = CCGP_EXP2_TAB[tid];
 
     const int64_t nitems = M.P * M.nchunks;
     for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
@@ -76,7 +78,7 @@ __global__ void __launch_bounds__(128) me_schur_kernel(const MeArgs M) {
                 double s = 0.0;
 #pragma unroll
                 for (int dd = 0; dd < DM; ++dd) { double df = Xo[dd * NOLD + j] - Xo[dd * NOLD + k]; s = fma(df, df, s); }
-                v = fma(cb, dexp_neg_dev<true>(t2 * s), ca * dexp_neg_dev<true>(t1 * s));
+                v = fma(cb, dexp_neg_tab_dev<true>(t2 * s, etab), ca * dexp_neg_tab_dev<true>(t1 * s, etab));
             }
             Lo[e] = v;
         }
@@ -120,7 +122,7 @@ __global__ void __launch_bounds__(128) me_schur_kernel(const MeArgs M) {
                 double s = 0.0;
 #pragma unroll
                 for (int dd = 0; dd < DM; ++dd) { double df = x[dd] - Xo[dd * NOLD + j]; s = fma(df, df, s); }
-                a[j] = (j < n_old) ? fma(cb, dexp_neg_dev<true>(t2 * s), ca * dexp_neg_dev<true>(t1 * s)) : 0.0;
+                a[j] = (j < n_old) ? fma(cb, dexp_neg_tab_dev<true>(t2 * s, etab), ca * dexp_neg_tab_dev<true>(t1 * s, etab)) : 0.0;
             }
 #pragma unroll
             for (int j = 0; j < NOLD; ++j) {
@@ -143,7 +145,9 @@ __global__ void __launch_bounds__(128) me_schur_kernel(const MeArgs M) {
                     const double df = x[dd] - xc;
                     sq = fma(df, df, sq);
                 }
-                double v = fma(cb, dexp_neg_dev<true>(t2 * sq), ca * dexp_neg_dev<true>(t1 * sq));
+                // entries c2 > r are never read and (r, r) is the unit diagonal: column n_new-1 needs no exponential
+                double v = 1.0;
+                if (c2 + 1 < n_new) v = fma(cb, dexp_neg_tab_dev<true>(t2 * sq, etab), ca * dexp_neg_tab_dev<true>(t1 * sq, etab));
                 if (c2 == r) v = 1.0;
                 const double* other = &abuf[warp][(lane & ~7) + c2][0];
                 double dot = 0.0;
@@ -204,8 +208,15 @@ inline int me_fast_launch(cudaStream_t stream, int num_sm, const double* d_D_old
     M.negdet = d_negdet; M.logdet = d_logdet; M.status = d_status;
     const int64_t items = P * M.nchunks;
     const int grid = (int)std::min<int64_t>(items, (int64_t)num_sm * 8);
-    if (n_old <= 16) me_schur_kernel<16><<<grid, 128, 0, stream>>>(M);
-    else me_schur_kernel<32><<<grid, 128, 0, stream>>>(M);
+    // 14 = the reference's initial design ([M]:980); d = 2 in the shipped script
+#define CCGP_ME_LAUNCH(NO) do { if (d <= 2) me_schur_kernel<NO, 2><<<grid, 128, 0, stream>>>(M); \
+                                else me_schur_kernel<NO, 4><<<grid, 128, 0, stream>>>(M); } while (0)
+    if (n_old <= 8) CCGP_ME_LAUNCH(8);
+    else if (n_old <= 14) CCGP_ME_LAUNCH(14);
+    else if (n_old <= 16) CCGP_ME_LAUNCH(16);
+    else if (n_old <= 24) CCGP_ME_LAUNCH(24);
+    else CCGP_ME_LAUNCH(32);
+#undef CCGP_ME_LAUNCH
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { snprintf(err, errlen, "me_schur_kernel launch: %s", cudaGetErrorString(e)); return -2; }
     return 0;
