@@ -227,6 +227,16 @@ class Engine:
                                                     family, _ptr(params), _ptr(out), _ptr(status)))
         return out, status
 
+    def kmedoids_pam(self, P, k, max_swaps=1000):
+        """PAM k-medoids of the rows of P (Euclidean) -> (medoid row indices[k], total cost, swaps)."""
+        P = _f(np.atleast_2d(P))
+        n, d = P.shape
+        med = np.empty(k, dtype=np.int32)
+        cost = np.zeros(1)
+        swaps = np.zeros(1, dtype=np.int32)
+        self._ck(self._lib.ccgp_kmedoids_pam(self._h, _ptr(P), n, d, int(k), int(max_swaps), _ptr(med), _ptr(cost), _ptr(swaps)))
+        return med, float(cost[0]), int(swaps[0])
+
     def mixed_corr(self, params, family, A, B=None):
         """Mixed correlation block between the rows of A and of B (B=None: A with itself)."""
         A = _f(np.atleast_2d(A))

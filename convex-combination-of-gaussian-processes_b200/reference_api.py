@@ -264,3 +264,15 @@ def Batch_Entropy_optim(D_old, n_new, d, p, theta1, theta2, n_starts, rng=None, 
 def Entropy_optim(n, d, p, theta1, theta2, n_starts, rng=None, engine=None, maxiter=200):
     """[M]:886-912: first-batch ME design (no D.old)."""
     return Batch_Entropy_optim(None, n, d, p, theta1, theta2, n_starts, rng, engine, maxiter)
+
+
+def kmedoids_design(D_old, subdesigns, k, engine=None):
+    """The clustering step behind `k-medoids ME Design.txt` (reference ReadMe.md:54-60): k-medoids
+    (cluster::pam) over the points of all second-batch designs; the medoids, appended to D.old, are
+    the next batch.  subdesigns: (C, n_new, d) or (C*n_new, d).  -> dict(Design, medoid_rows, cost)."""
+    eng = engine or default_engine()
+    P = np.asarray(subdesigns, dtype=np.float64)
+    P = P.reshape(-1, P.shape[-1])
+    med, cost, _ = eng.kmedoids_pam(P, k)
+    D_old = np.atleast_2d(np.asarray(D_old, dtype=np.float64))
+    return dict(Design=np.vstack([D_old, P[med]]), medoid_rows=med, cost=cost)

@@ -154,6 +154,14 @@ int ccgp_me_argmin(ccgp_ctx* ctx, const double* D_old, int n_old, int d,
                    const double* params, int64_t P, int64_t ldq,
                    double* best_val, int64_t* best_idx);
 
+/* k-medoids (PAM: BUILD + steepest SWAP, Euclidean distance) of n points (n x d column-major,
+ * host): the clustering step that condenses the 1000 second-batch designs of All_Subdesigns.txt
+ * into `k-medoids ME Design.txt` (reference ReadMe.md:54-60; R's cluster::pam).
+ *   out_medoids[k]: 0-based row indices of the medoids (BUILD order, exchanged in place by SWAP)
+ *   out_cost: sum of distances to the nearest medoid; out_swaps: exchanges performed (either may be NULL) */
+int ccgp_kmedoids_pam(ccgp_ctx* ctx, const double* P, int64_t n, int d, int k, int max_swaps,
+                      int32_t* out_medoids, double* out_cost, int32_t* out_swaps);
+
 /* log det R[S,S] for C index subsets (0-based, C x m column-major, ldi >= C) of a
  * pool of N points (N x d column-major): the ME subset log-dets of the scaling
  * case.  One natural-scale parameter row of `family`. */

@@ -577,3 +577,59 @@ def test_function(code, x, y):
     if code == 5:
         return np.sin(9 * x - 4.5) / (9 * x - 4.5) * np.sin(12 * y - 6) / (12 * y - 6)
     raise ValueError(code)
+
+
+# ---------------------------------------------------------------------------------------------
+# k-medoids (PAM) -- the step between All_Subdesigns.txt and `k-medoids ME Design.txt`
+# (reference ReadMe.md:54-60; the script that ran it is not shipped).  R's cluster::pam is an
+# un-vendored CRAN dependency with no pinned version; this restates its published algorithm
+# (Kaufman & Rousseeuw 1990, ch. 2: BUILD, then SWAP by steepest descent) with Euclidean
+# distances.  Pinned by the shipped files: on the 7000 points of All_Subdesigns.txt it ends at
+# exactly rows 15-21 of `k-medoids ME Design.txt` (tests/test_kmedoids.py).
+def pam_kmedoids(P, k, max_swaps=1000, trace=None):
+    P = np.asarray(P, dtype=np.float64)
+    n = P.shape[0]
+    D = np.zeros((n, n))
+    for kk in range(P.shape[1]):                       # sum over coordinates in order, no FMA (as the device)
+        df = P[:, kk][:, None] - P[:, kk][None, :]
+        D += df * df
+    np.sqrt(D, out=D)
+    med = [int(np.argmin(D.sum(axis=0)))]
+    near = D[:, med[0]].copy()
+    while len(med) < k:
+        gain = np.zeros(n)
+        for lo in range(0, n, 1024):                   # blocked: bounds the temporary
+            gain[lo:lo + 1024] = np.maximum(near[:, None] - D[:, lo:lo + 1024], 0.0).sum(axis=0)
+        gain[med] = -np.inf
+        h = int(np.argmax(gain))
+        med.append(h)
+        near = np.minimum(near, D[:, h])
+    if trace is not None:
+        trace.append(("build", list(med)))
+    swaps = 0
+    while swaps < max_swaps and k < n:
+        Dm = D[:, med]
+        order = np.argsort(Dm, axis=1, kind="stable")
+        nearest = order[:, 0]
+        d1 = Dm[np.arange(n), nearest]
+        d2 = Dm[np.arange(n), order[:, 1]] if k > 1 else np.full(n, np.inf)
+        cur = d1.sum()
+        best = (0.0, None, None)
+        for i in range(k):
+            base = np.where(nearest == i, d2, d1)
+            newcost = np.empty(n)
+            for lo in range(0, n, 1024):
+                newcost[lo:lo + 1024] = np.minimum(base[:, None], D[:, lo:lo + 1024]).sum(axis=0)
+            newcost[med] = np.inf
+            h = int(np.argmin(newcost))
+            delta = newcost[h] - cur
+            if delta < best[0] and delta < -1e-12 * cur:
+                best = (delta, i, h)
+        if best[1] is None:
+            break
+        med[best[1]] = best[2]
+        swaps += 1
+        if trace is not None:
+            trace.append(("swap", best[1], best[2]))
+    cost = D[:, med].min(axis=1).sum()
+    return np.array(med, dtype=np.int32), float(cost), swaps

@@ -155,3 +155,12 @@ Metro.multichain <- function(pars, N, samp.size, batch.size, alpha, D.train, sig
     list(sample = data.frame(samp[c, rows, ]), beta = beta[c, rows])
   })
 }
+
+# ---- k-medoids design (reference ReadMe.md:54-60) ------------------------------------------------
+# 7-medoids (cluster::pam) over the points of all second-batch designs -> the next batch.
+# subdesigns: (C * n.new) x d matrix (the layout of All_Subdesigns.txt).
+kmedoids.design <- function(D.old, subdesigns, k) {
+  P <- matrix(as.double(as.matrix(subdesigns)), nrow = nrow(subdesigns))
+  r <- .Call("ccgp_R_kmedoids_pam", .ccgp$ctx, P, as.integer(k), 1000L)   # list(medoid rows (1-based), cost, swaps)
+  list(Design = rbind(as.matrix(D.old), P[r[[1]], , drop = FALSE]), medoid.rows = r[[1]], cost = r[[2]])
+}

@@ -132,3 +132,20 @@ SEXP ccgp_R_mixed_corr(SEXP ptr, SEXP family, SEXP params, SEXP A, SEXP B) {
     check(ctx, rc, "mixed_corr");
     return out;
 }
+
+/* PAM k-medoids of the rows of P (n x d).  Returns list(medoid rows (1-based), cost, swaps). */
+SEXP ccgp_R_kmedoids_pam(SEXP ptr, SEXP P, SEXP k_, SEXP max_swaps) {
+    ccgp_ctx* ctx = get_ctx(ptr);
+    int k = Rf_asInteger(k_);
+    SEXP med = PROTECT(Rf_allocVector(INTSXP, k));
+    SEXP cost = PROTECT(Rf_allocVector(REALSXP, 1));
+    SEXP swaps = PROTECT(Rf_allocVector(INTSXP, 1));
+    int rc = ccgp_kmedoids_pam(ctx, REAL(P), (int64_t)Rf_nrows(P), Rf_ncols(P), k, Rf_asInteger(max_swaps),
+                               (int32_t*)INTEGER(med), REAL(cost), (int32_t*)INTEGER(swaps));
+    for (int i = 0; i < k; ++i) INTEGER(med)[i] += 1;
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 3));
+    SET_VECTOR_ELT(out, 0, med); SET_VECTOR_ELT(out, 1, cost); SET_VECTOR_ELT(out, 2, swaps);
+    UNPROTECT(4);
+    check(ctx, rc, "kmedoids_pam");
+    return out;
+}
