@@ -7,6 +7,6 @@ from ._capi import CcgpError, LIB_PATH, SYMBOLS  # noqa: F401
 from .engine import (Engine, GAUSS_ISO, GAUSS_ANISO_LAMBDA, GAUSS_ISO_RAW2, MATERN1D, MATERN_SPLINE1D,  # noqa: F401
                      NATURAL, LOGSCALE,
                      MEAN_GLS_BETA, MEAN_ZERO_PLUS_TAU2)
-from . import reference_api, workloads, sharding, samplers  # noqa: F401
+from . import reference_api, workloads, sharding, samplers, me_design  # noqa: F401
 
-__all__ = ["Engine", "CcgpError", "reference_api", "workloads", "sharding", "samplers"]
+__all__ = ["Engine", "CcgpError", "reference_api", "workloads", "sharding", "samplers", "me_design"]

@@ -677,6 +677,44 @@ extern "C" int ccgp_me_schur_batch(ccgp_ctx* ctx, const double* D_old, int n_old
     return CCGP_OK;
 }
 
+// paired form: design c is evaluated against parameter row c / group only (C = P * group) -- the shape of a
+// lock-step optimiser over (posterior draw, start) pairs, each with its own stencil of designs
+extern "C" int ccgp_me_schur_paired(ccgp_ctx* ctx, const double* D_old, int n_old, int d, const double* D_new, int n_new,
+                                    int64_t group, const double* params, int64_t P, int64_t ldq, double* out_negdet,
+                                    int32_t* out_status) {
+    if (!ctx) return CCGP_ERR_ARG;
+    ARG(n_old >= 0 && n_new >= 1 && d >= 1 && d <= MAXD && group >= 1 && P >= 0 && ldq >= P);
+    if (P == 0) return CCGP_OK;
+    ARG(D_new && params && out_negdet);
+    ARG(n_old == 0 || D_old != nullptr);
+    if (!me_fast_supported(n_old, n_new, d)) {
+        snprintf(ctx->err, sizeof(ctx->err), "ccgp_me_schur_paired: sizes beyond the ME kernel (n_new <= 8, n_old <= 32, d <= 4)");
+        return CCGP_ERR_UNSUPPORTED;
+    }
+    CK(cudaSetDevice(ctx->device));
+    const int64_t C = P * group;
+    size_t nold_d = (size_t)n_old * d, nnew = (size_t)C * n_new * d, npar = (size_t)P * 3, nout = (size_t)C;
+    size_t need = (nold_d + nnew + npar + nout) * 8 + nout * 4;
+    int rc = ensure_ws(ctx, need);
+    if (rc) return rc;
+    double* d_old = (double*)ctx->ws;
+    double* d_new = d_old + nold_d;
+    double* d_par = d_new + nnew;
+    double* d_neg = d_par + npar;
+    int32_t* d_st = (int32_t*)(d_neg + nout);
+    if (n_old) CK(cudaMemcpyAsync(d_old, D_old, nold_d * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_new, D_new, nnew * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpy2DAsync(d_par, (size_t)P * 8, params, (size_t)ldq * 8, (size_t)P * 8, 3, cudaMemcpyHostToDevice, ctx->stream));
+    rc = me_fast_launch(ctx->stream, ctx->num_sm, d_old, n_old, d, d_new, n_new, C, d_par, P, P, d_neg, nullptr, d_st,
+                        ctx->err, sizeof(ctx->err), group);
+    if (rc) return rc;
+    ctx->launches++;
+    CK(cudaMemcpyAsync(out_negdet, d_neg, nout * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_status) CK(cudaMemcpyAsync(out_status, d_st, nout * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return CCGP_OK;
+}
+
 extern "C" int ccgp_me_argmin(ccgp_ctx* ctx, const double* D_old, int n_old, int d, const double* D_new, int n_new,
                               int64_t C, const double* params, int64_t P, int64_t ldq, double* best_val,
                               int64_t* best_idx) {

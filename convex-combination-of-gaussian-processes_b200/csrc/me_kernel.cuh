@@ -27,7 +27,8 @@ struct MeArgs {
     int n_old, n_new, d;
     int64_t C, P;
     int64_t chunk;         // candidates per work item
-    int64_t nchunks;       // ceil(C / chunk)
+    int64_t nchunks;       // ceil(candidates per parameter row / chunk)
+    int64_t group;         // 0: every design x every parameter row; G > 0: designs [qG, (q+1)G) belong to row q (C = P G)
     double* negdet;        // C x P column-major (may be NULL)
     double* logdet;        // (may be NULL)
     int32_t* status;       // (may be NULL)
@@ -106,7 +107,8 @@ __global__ void __launch_bounds__(128) me_schur_kernel(const MeArgs M) {
         const int bad_old = s_bad;
 
         // ---- candidates of this chunk: 16 per pass (4 warps x 4 groups) -----------------------
-        const int64_t c_lo = ch * M.chunk, c_hi = min(M.C, c_lo + M.chunk);
+        const int64_t c_beg = M.group ? q * M.group : 0, c_end = M.group ? c_beg + M.group : M.C;
+        const int64_t c_lo = c_beg + ch * M.chunk, c_hi = min(c_end, c_lo + M.chunk);
         for (int64_t c0 = c_lo; c0 < c_hi; c0 += 16) {
             const int64_t c = c0 + warp * 4 + grp;
             const bool valid = c < c_hi;
@@ -182,7 +184,7 @@ __global__ void __launch_bounds__(128) me_schur_kernel(const MeArgs M) {
                 for (int c2 = cc + 1; c2 < 8; ++c2) s8[c2] = fma(-l, lc2[c2], s8[c2]);
             }
             if (valid && r == 0) {
-                const int64_t o = c + M.C * q;
+                const int64_t o = M.group ? c : c + M.C * q;
                 const double nanv = __longlong_as_double(0x7ff8000000000000LL);
                 if (M.negdet) M.negdet[o] = bad ? nanv : -scalbn(mant, es);
                 if (M.logdet) M.logdet[o] = bad ? nanv : log(mant) + es * LN2;
@@ -195,16 +197,19 @@ __global__ void __launch_bounds__(128) me_schur_kernel(const MeArgs M) {
 
 inline int me_fast_launch(cudaStream_t stream, int num_sm, const double* d_D_old, int n_old, int d,
                           const double* d_D_new, int n_new, int64_t C, const double* d_params, int64_t P,
-                          int64_t ldq, double* d_negdet, double* d_logdet, int32_t* d_status, char* err, size_t errlen) {
+                          int64_t ldq, double* d_negdet, double* d_logdet, int32_t* d_status, char* err, size_t errlen,
+                          int64_t group = 0) {
     MeArgs M;
+    M.group = group;
+    const int64_t Cq = group ? group : C;                  // candidates per parameter row
     M.D_old = d_D_old; M.D_new = d_D_new; M.params = d_params; M.ldq = ldq;
     M.n_old = n_old; M.n_new = n_new; M.d = d; M.C = C; M.P = P;
     // enough candidates per work item to amortise the R.old factorisation, enough items to fill the GPU
     int64_t chunk = 256;
     const int64_t target_items = (int64_t)num_sm * 8;
-    while (chunk > 16 && P * ((C + chunk - 1) / chunk) < target_items) chunk >>= 1;
+    while (chunk > 16 && P * ((Cq + chunk - 1) / chunk) < target_items) chunk >>= 1;
     M.chunk = chunk;
-    M.nchunks = (C + chunk - 1) / chunk;
+    M.nchunks = (Cq + chunk - 1) / chunk;
     M.negdet = d_negdet; M.logdet = d_logdet; M.status = d_status;
     const int64_t items = P * M.nchunks;
     const int grid = (int)std::min<int64_t>(items, (int64_t)num_sm * 8);

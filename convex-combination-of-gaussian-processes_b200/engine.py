@@ -227,6 +227,24 @@ class Engine:
                                                     family, _ptr(params), _ptr(out), _ptr(status)))
         return out, status
 
+    def me_schur_paired(self, D_old, D_new, params, group):
+        """Design c against parameter row c // group only: D_new (P*group, n_new, d) -> negdet[P*group], status."""
+        blocks, (Cn, n_new, d) = self._pack_designs(D_new)
+        params = _f(np.atleast_2d(params))
+        P = params.shape[0]
+        if Cn != P * group:
+            raise ValueError("need P * group designs")
+        if D_old is None or len(D_old) == 0:
+            Do, n_old = None, 0
+        else:
+            Do = _f(np.atleast_2d(D_old))
+            n_old = Do.shape[0]
+        negdet = np.empty(Cn)
+        status = np.empty(Cn, dtype=np.int32)
+        self._ck(self._lib.ccgp_me_schur_paired(self._h, _ptr(Do), n_old, d, _ptr(blocks), n_new, int(group), _ptr(params), P, P,
+                                                _ptr(negdet), _ptr(status)))
+        return negdet, status
+
     def kmedoids_pam(self, P, k, max_swaps=1000):
         """PAM k-medoids of the rows of P (Euclidean) -> (medoid row indices[k], total cost, swaps)."""
         P = _f(np.atleast_2d(P))

@@ -147,6 +147,14 @@ int ccgp_me_schur_batch_dev(ccgp_ctx* ctx, const double* d_D_old, int n_old, int
                             const double* d_D_new, int n_new, int64_t C,
                             const double* d_params, int64_t P, int64_t ldq,
                             double* d_negdet, double* d_logdet, int32_t* d_status);
+/* Paired form of the criterion: C = P * group designs, design c evaluated against parameter row
+ * c / group only (out_negdet[C]).  This is the shape `Batch.Entropy.optim` ([M]:920-948) takes when
+ * it is run for many posterior draws and starts in lock-step: each (draw, start) brings its own
+ * finite-difference stencil of designs. */
+int ccgp_me_schur_paired(ccgp_ctx* ctx, const double* D_old, int n_old, int d,
+                         const double* D_new, int n_new, int64_t group,
+                         const double* params, int64_t P, int64_t ldq,
+                         double* out_negdet, int32_t* out_status);
 /* which.min over the candidates of each parameter row ([M]:944-945):
  * best_idx[q] = first c minimising out_negdet[c,q], best_val[q] its value. */
 int ccgp_me_argmin(ccgp_ctx* ctx, const double* D_old, int n_old, int d,

@@ -164,3 +164,8 @@ kmedoids.design <- function(D.old, subdesigns, k) {
   r <- .Call("ccgp_R_kmedoids_pam", .ccgp$ctx, P, as.integer(k), 1000L)   # list(medoid rows (1-based), cost, swaps)
   list(Design = rbind(as.matrix(D.old), P[r[[1]], , drop = FALSE]), medoid.rows = r[[1]], cost = r[[2]])
 }
+
+# paired criterion for lock-step optimisers over (posterior draw, start) pairs: column c of the
+# (n.new*d) x (P*group) matrix of c(D.new) vectors is evaluated against params[c %/% group + 1, ] only
+entropy.paired <- function(D.old, D.new.cols, n.new, d, params, group)
+  .Call("ccgp_R_me_schur_paired", .ccgp$ctx, D.old, D.new.cols, as.integer(n.new), as.integer(d), params, as.integer(group))[[1]]

@@ -149,3 +149,22 @@ SEXP ccgp_R_kmedoids_pam(SEXP ptr, SEXP P, SEXP k_, SEXP max_swaps) {
     check(ctx, rc, "kmedoids_pam");
     return out;
 }
+
+/* Paired ME criterion: D.new is (n_new*d) x (P*group), column c belongs to parameter row c %/% group.
+ * Returns list(negdet (P*group), status). */
+SEXP ccgp_R_me_schur_paired(SEXP ptr, SEXP D_old, SEXP D_new, SEXP n_new_, SEXP d_, SEXP params, SEXP group_) {
+    ccgp_ctx* ctx = get_ctx(ptr);
+    int n_new = Rf_asInteger(n_new_), d = Rf_asInteger(d_);
+    int n_old = Rf_isNull(D_old) ? 0 : Rf_nrows(D_old);
+    int64_t C = Rf_ncols(D_new), P = Rf_nrows(params), group = Rf_asInteger(group_);
+    if (C != P * group) Rf_error("ccgp: need nrow(params) * group designs");
+    SEXP negdet = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)C));
+    SEXP status = PROTECT(Rf_allocVector(INTSXP, (R_xlen_t)C));
+    int rc = ccgp_me_schur_paired(ctx, n_old ? REAL(D_old) : NULL, n_old, d, REAL(D_new), n_new, group, REAL(params), P, P,
+                                  REAL(negdet), (int32_t*)INTEGER(status));
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 2));
+    SET_VECTOR_ELT(out, 0, negdet); SET_VECTOR_ELT(out, 1, status);
+    UNPROTECT(3);
+    check(ctx, rc, "me_schur_paired");
+    return out;
+}
