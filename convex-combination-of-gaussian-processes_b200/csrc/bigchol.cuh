@@ -16,6 +16,7 @@
 // rows ncp and ncp+1 are y' and 1', zero rows up to nrp = ncp + 64.
 #pragma once
 #include <algorithm>
+#include <stdlib.h>
 #include "factor_engine.cuh"
 #include "bigchol_ws.h"
 
@@ -30,6 +31,7 @@ struct BigArgs {
     const Prm* prm;
     double* logdet;
     int* bad;
+    double* linv;              // per candidate: inv(L_kk)' of the block just factored, linv[q*64 + c] = inv(L_kk)(c, q)
 };
 
 __global__ void __launch_bounds__(128) big_params_kernel(FactorArgs F, int64_t b0, int nb, Prm* prm, double* logdet, int* bad) {
@@ -111,6 +113,22 @@ __global__ void __launch_bounds__(256) big_potrf_kernel(BigArgs G, int k) {
     if (tid == 0) {
         G.logdet[b] += ld;
         if (s_bad) G.bad[b] = 1;
+    }
+    // inverse of the factored block, column per thread (forward substitution on e_j); stored transposed so the
+    // rows below become a product X = A inv(L_kk)' on the tensor path (big_update_kernel, TRSM mode)
+    if (tid < 64) {
+        const int j = tid;
+        double* out = G.linv + (size_t)b * 4096;
+        double x[64];
+#pragma unroll
+        for (int r = 0; r < 64; ++r) {
+            double s = (r == j) ? 1.0 : 0.0;
+#pragma unroll
+            for (int q = 0; q < r; ++q) s = fma(-S[q * 65 + r], x[q], s);      // L(r, q) at S[q*65 + r]
+            x[r] = (r >= j) ? s / S[r * 65 + r] : 0.0;
+        }
+#pragma unroll
+        for (int r = 0; r < 64; ++r) out[(size_t)j * 64 + r] = x[r];            // linv[q = j][c = r] = inv(L)(r, j)
     }
 }
 
@@ -196,6 +214,100 @@ __global__ void __launch_bounds__(128) big_syrk_kernel(BigArgs G, int k, int nti
         }
 }
 
+// ---- left-looking update of block column k (all row tiles at once, every previous panel in one launch) ----
+//   C(rows, k) -= sum_{j<k} L(rows, j) L(k, j)'        rows: 128-row tiles from the diagonal block down to y', 1'
+// The accumulators stay in registers over the whole K = 64 k contraction (the right-looking big_syrk_kernel
+// re-read and re-wrote every trailing tile once per panel: HBM-bound at 2 FMA per byte).  256 threads = 8 warps
+// (4 x 2), each a 32x32 quadrant = 4x4 DMMA m8n8k4 fragments; operands travel HBM/L2 -> shared memory in
+// 32-column chunks with cp.async, double buffered (the chunk after next is in flight while this one is
+// multiplied); k-major staging with leading dimensions 136 / 72 (k-stride = 64 B mod 128 B) keeps every fragment
+// load conflict-free.
+constexpr int BU_KC = 32, BU_LDA = 136, BU_LDB = 72;
+constexpr int BU_STAGE = BU_KC * (BU_LDA + BU_LDB);           // doubles per stage
+__device__ __forceinline__ void cp_async16(double* dst_smem, const double* src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+}
+// TRSM = true: rows below the diagonal block of column k, X = A inv(L_kk)' (K = 64, B operand = G.linv), in place.
+template <bool TRSM>
+__global__ void __launch_bounds__(256, 2) big_update_kernel(BigArgs G, int k) {
+    extern __shared__ __align__(16) double sm[];
+    const int b = blockIdx.y, tid = threadIdx.x;
+    const int row0 = (TRSM ? (k + 1) * 64 : k * 64) + blockIdx.x * 128;   // first row of this tile
+    const int rows_here = min(128, G.nrp - row0);                     // 128 or 64
+    const double* Ab = G.A + (size_t)b * G.stride;
+    const int nch = TRSM ? 2 : 2 * k;                                 // 32-column chunks: panels 0..k-1, or block column k itself
+    const double* Lt = G.linv + (size_t)b * 4096;
+    auto load = [&](int stage, int ch) {
+        double* As = sm + stage * BU_STAGE;
+        double* Bs = As + BU_KC * BU_LDA;
+        const size_t col0 = (size_t)ch * BU_KC + (TRSM ? (size_t)k * 64 : 0);
+        for (int e = tid; e < BU_KC * 64; e += 256) {                 // A: 32 columns x 64 chunks of 2 rows
+            const int kk = e >> 6, r2 = (e & 63) * 2;
+            double* dst = As + kk * BU_LDA + r2;
+            if (r2 < rows_here) cp_async16(dst, Ab + (col0 + kk) * G.nrp + row0 + r2);
+            else { dst[0] = 0.0; dst[1] = 0.0; }
+        }
+        for (int e = tid; e < BU_KC * 32; e += 256) {                 // B: rows of block k
+            const int kk = e >> 5, r2 = (e & 31) * 2;
+            if (TRSM) cp_async16(Bs + kk * BU_LDB + r2, Lt + (size_t)(ch * BU_KC + kk) * 64 + r2);
+            else cp_async16(Bs + kk * BU_LDB + r2, Ab + (col0 + kk) * G.nrp + (size_t)k * 64 + r2);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    const int warp = tid >> 5, lane = tid & 31;
+    const int wr = (warp >> 1) * 32, wc = (warp & 1) * 32;
+    const int fr = lane >> 2, fk = lane & 3;
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+    load(0, 0);
+    for (int ch = 0; ch < nch; ++ch) {
+        if (ch + 1 < nch) {
+            load((ch + 1) & 1, ch + 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        const double* As = sm + (ch & 1) * BU_STAGE;
+        const double* Bs = As + BU_KC * BU_LDA;
+#pragma unroll
+        for (int k0 = 0; k0 < BU_KC; k0 += 4) {
+            double af[4], bf[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) af[i] = As[(k0 + fk) * BU_LDA + wr + 8 * i + fr];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bf[j] = Bs[(k0 + fk) * BU_LDB + wc + 8 * j + fr];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+        __syncthreads();
+    }
+    double* C = G.A + (size_t)b * G.stride + (size_t)(k * 64) * G.nrp + row0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = wr + 8 * i + fr;
+        if (r < rows_here) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = wc + 8 * j + 2 * fk;
+                if (TRSM) {
+                    C[(size_t)c * G.nrp + r] = acc[i][j][0];
+                    C[(size_t)(c + 1) * G.nrp + r] = acc[i][j][1];
+                } else {
+                    C[(size_t)c * G.nrp + r] -= acc[i][j][0];
+                    C[(size_t)(c + 1) * G.nrp + r] -= acc[i][j][1];
+                }
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) big_finish_kernel(BigArgs G, int64_t b0, double sigma2, int mean_mode, double tau,
                                                         double* out_nll, double* out_beta, int32_t* out_status) {
     __shared__ double red[64];
@@ -252,10 +364,13 @@ inline int bigchol_nll_batch(BigCholWorkspace& ws, cudaStream_t stream, int num_
         BIGCK(cudaMalloc(&ws.logdet, (size_t)chunk * 8));
         BIGCK(cudaMalloc(&ws.bad, (size_t)chunk * 4));
         BIGCK(cudaMalloc(&ws.prm, (size_t)chunk * sizeof(Prm)));
+        BIGCK(cudaMalloc(&ws.linv, (size_t)chunk * 4096 * 8));
         ws.bytesA = (size_t)chunk * per;
         ws.cap = chunk;
     }
     BIGCK(cudaFuncSetAttribute(big_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 64 * 72 * 8));
+    BIGCK(cudaFuncSetAttribute(big_update_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * BU_STAGE * 8));
+    BIGCK(cudaFuncSetAttribute(big_update_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * BU_STAGE * 8));
     BIGCK(cudaFuncSetAttribute(big_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 64 * 65 * 8));
     FactorArgs F;
     memset(&F, 0, sizeof(F));
@@ -263,19 +378,26 @@ inline int bigchol_nll_batch(BigCholWorkspace& ws, cudaStream_t stream, int num_
     F.force_clamp = 1;
     BigArgs G;
     G.A = ws.A; G.n = n; G.d = d; G.ncp = ncp; G.nrp = nrp; G.stride = (int64_t)nrp * ncp;
-    G.X = d_X; G.y = d_y; G.prm = ws.prm; G.logdet = ws.logdet; G.bad = ws.bad;
+    G.X = d_X; G.y = d_y; G.prm = ws.prm; G.logdet = ws.logdet; G.bad = ws.bad; G.linv = ws.linv;
     for (int64_t b0 = 0; b0 < B; b0 += chunk) {
         const int nb = (int)std::min<int64_t>(chunk, B - b0);
         big_params_kernel<<<(nb + 127) / 128, 128, 0, stream>>>(F, b0, nb, ws.prm, ws.logdet, ws.bad);
         big_build_kernel<<<dim3(T, T + 1, nb), 256, 0, stream>>>(G);
         *launches += 2;
+        const bool right_looking = getenv("CCGP_BIG_RIGHT") && atoi(getenv("CCGP_BIG_RIGHT"));   // the old schedule, for A/B runs
         for (int k = 0; k < T; ++k) {
+            if (!right_looking && k > 0) {
+                const int nrt = (nrp - k * 64 + 127) / 128;
+                big_update_kernel<false><<<dim3(nrt, nb), 256, 2 * BU_STAGE * 8, stream>>>(G, k);
+                *launches += 1;
+            }
             big_potrf_kernel<<<nb, 256, 0, stream>>>(G, k);
             const int rt = (nrp - (k + 1) * 64) / 64;           // row tiles below the diagonal block
-            if (rt > 0) big_trsm_kernel<<<dim3(rt, nb), 64, 2 * 64 * 65 * 8, stream>>>(G, k);
+            if (rt > 0 && right_looking) big_trsm_kernel<<<dim3(rt, nb), 64, 2 * 64 * 65 * 8, stream>>>(G, k);
+            else if (rt > 0) big_update_kernel<true><<<dim3((rt * 64 + 127) / 128, nb), 256, 2 * BU_STAGE * 8, stream>>>(G, k);
             *launches += 2;
             const int ct = T - (k + 1);                         // real block columns still to update
-            if (ct > 0) {
+            if (right_looking && ct > 0) {
                 // tiles (ti, tj) with tj < ct, ti in [tj, rt): sum_{tj<ct} (rt - tj)
                 const int ntiles = ct * rt - ct * (ct - 1) / 2;
                 big_syrk_kernel<<<dim3(ntiles, nb), 128, 2 * 64 * 72 * 8, stream>>>(G, k, rt);

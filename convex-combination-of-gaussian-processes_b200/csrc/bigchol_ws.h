@@ -10,6 +10,7 @@ struct BigCholWorkspace {
     double* logdet = nullptr;  // chunk
     int* bad = nullptr;        // chunk
     Prm* prm = nullptr;        // chunk
+    double* linv = nullptr;    // chunk * 64 * 64: inverse of the current diagonal block, transposed (k-major B operand)
     size_t bytesA = 0;
     int cap = 0;
     void release() {
@@ -17,7 +18,8 @@ struct BigCholWorkspace {
         if (logdet) cudaFree(logdet);
         if (bad) cudaFree(bad);
         if (prm) cudaFree(prm);
-        A = nullptr; logdet = nullptr; bad = nullptr; prm = nullptr; bytesA = 0; cap = 0;
+        if (linv) cudaFree(linv);
+        A = nullptr; logdet = nullptr; bad = nullptr; prm = nullptr; linv = nullptr; bytesA = 0; cap = 0;
     }
 };
 
