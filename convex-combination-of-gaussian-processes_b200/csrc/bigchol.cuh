@@ -81,34 +81,59 @@ __global__ void __launch_bounds__(256) big_build_kernel(BigArgs G) {
 // 64x64 Cholesky of diagonal block k in shared memory; one CTA per candidate
 __global__ void __launch_bounds__(256) big_potrf_kernel(BigArgs G, int k) {
     __shared__ double S[64 * 65];
-    __shared__ double s_ri;
     __shared__ int s_bad;
     const int b = blockIdx.x, tid = threadIdx.x;
     double* Ab = G.A + (size_t)b * G.stride + (size_t)(k * 64) * G.nrp + k * 64;
     for (int e = tid; e < 4096; e += 256) { int r = e % 64, c = e / 64; S[c * 65 + r] = Ab[(size_t)c * G.nrp + r]; }
     if (tid == 0) s_bad = 0;
     __syncthreads();
+    // blocked in 8-column panels: warp 0 factors the panel (lane <-> rows lane, lane+32; warp-synchronous, no
+    // CTA barrier per column), then all 256 threads apply its rank-8 update to the trailing block
     double ld = 0.0;
-    for (int j = 0; j < 64; ++j) {
-        if (tid == 0) {
-            const double piv = S[j * 65 + j];
-            const bool live = (k * 64 + j) < G.n;
-            if (live && !(piv > PIVOT_MIN)) s_bad = 1;
-            if (live) ld += log(piv);
-            const double ri = fast_rsqrt(piv);
-            s_ri = ri;
-            S[j * 65 + j] = piv * ri;
+    int bad = 0;
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int j0 = 0; j0 < 64; j0 += 8) {
+        if (warp == 0) {
+            for (int c = j0; c < j0 + 8; ++c) {
+                const double piv = S[c * 65 + c];
+                const bool live = (k * 64 + c) < G.n;
+                if (live && !(piv > PIVOT_MIN)) bad = 1;
+                if (live && lane == 0) ld += log(piv);
+                const double ri = fast_rsqrt(piv);
+                __syncwarp();
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int r = lane + 32 * h;
+                    if (r > c) S[c * 65 + r] *= ri;
+                    else if (r == c) S[c * 65 + r] = piv * ri;
+                }
+                __syncwarp();
+                for (int c2 = c + 1; c2 < j0 + 8; ++c2) {
+                    const double lc = S[c * 65 + c2];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int r = lane + 32 * h;
+                        if (r >= c2) S[c2 * 65 + r] = fma(-S[c * 65 + r], lc, S[c2 * 65 + r]);
+                    }
+                }
+                __syncwarp();
+            }
         }
         __syncthreads();
-        const double ri = s_ri;
-        if (tid > j && tid < 64) S[j * 65 + tid] *= ri;
-        __syncthreads();
-        for (int e = tid; e < 4096; e += 256) {
-            const int r = e % 64, c = e / 64;
-            if (c > j && r >= c) S[c * 65 + r] = fma(-S[j * 65 + r], S[j * 65 + c], S[c * 65 + r]);
+        const int nt = 56 - j0;                                 // trailing block: columns/rows j0+8 .. 63
+        for (int e = tid; e < nt * nt; e += 256) {
+            const int c2 = j0 + 8 + e / nt, r = j0 + 8 + e % nt;
+            if (r >= c2) {
+                double v = S[c2 * 65 + r];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) v = fma(-S[(j0 + c) * 65 + r], S[(j0 + c) * 65 + c2], v);
+                S[c2 * 65 + r] = v;
+            }
         }
         __syncthreads();
     }
+    if (warp == 0 && __any_sync(0xffffffffu, bad) && lane == 0) s_bad = 1;
+    __syncthreads();
     for (int e = tid; e < 4096; e += 256) { int r = e % 64, c = e / 64; if (r >= c) Ab[(size_t)c * G.nrp + r] = S[c * 65 + r]; }
     if (tid == 0) {
         G.logdet[b] += ld;
