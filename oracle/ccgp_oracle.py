@@ -12,6 +12,8 @@ the R functions line by line, using the same LAPACK routines base R calls
 (dgesv+dgecon for `solve`, dgetrf for `det`, dpotrf/dpotri for `chol`/
 `chol2inv`), and is cross-checked three ways in tests/: reference-faithful path
 vs minimal (Cholesky) path vs a 50-digit mpmath truth.
+One piece IS pinned by shipped files: `pam_kmedoids` reproduces rows 15-21 of
+`k-medoids ME Design.txt` from `All_Subdesigns.txt` exactly (tests/test_kmedoids.py).
 
 File aliases (all under /root/reference):
   [A] 2D Codes and Designs/2D Combined GP Anisotropic Public.R

@@ -99,7 +99,7 @@ def test_every_kernel_variant_agrees(engine, golden, designs):
     engine.set_design(designs["maximin100"], golden["c1n100_y"])
     base = None
     try:
-        for v in range(21):
+        for v in range(5):
             os.environ["CCGP_VARIANT"] = str(v)
             nll, beta, st = engine.nll_batch(golden["c1n100_nat"], GAUSS_ANISO_LAMBDA, 1.0)
             assert np.all(st == 0), v
