@@ -12,6 +12,7 @@ sys.path.insert(0, ROOT)
 import ccgp_b200  # noqa: E402
 from ccgp_b200 import workloads, GAUSS_ANISO_LAMBDA, LOGSCALE  # noqa: E402
 
+os.environ.setdefault("CCGP_NO_MMA", "1")   # the DFMA kernel (factor_engine.cuh)
 eng = ccgp_b200.Engine(0)
 X, y, s2 = workloads.m1_design()
 eng.set_design(X, y)
