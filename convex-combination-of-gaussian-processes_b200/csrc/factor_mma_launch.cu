@@ -14,19 +14,14 @@ static const int g_num_mma_variants = sizeof(g_mma_variants) / sizeof(g_mma_vari
 // ---- one-warp-per-candidate DMMA kernel (factor_warp.cuh): MAXT = tiles of the first block column, even ----
 struct WarpVariant { int maxt, minb; factor_fn fn_d0, fn_d2; };
 #define WV(MT, MB) {MT, MB, factor_warp_kernel<MT, 0, MB>, factor_warp_kernel<MT, 2, MB>},
-static const WarpVariant g_warp_variants[] = {WV(4, 3) WV(8, 2) WV(14, 1)};
+static const WarpVariant g_warp_variants[] = {WV(4, 3) WV(8, 2) WV(10, 2) WV(14, 1)};
 #undef WV
 
 // ---- team kernel (factor_team.cuh): NW warps per candidate on one sub-partition; nrmax = most tile rows ----
-struct TeamVariant { int nw, nrmax, maxt; factor_fn fn_d0, fn_d2, fu_d0, fu_d2; };
-#define TV(NWv, NRM, MT, MB) {NWv, NRM, MT, factor_team_kernel<NWv, MT, 0, MB, false>, factor_team_kernel<NWv, MT, 2, MB, false>, \
-                              nullptr, nullptr},
-// the fused-build experiment (CCGP_TEAM_FUSED=1) is instantiated for the production team size only
-#define TVF(NWv, NRM, MT, MB) {NWv, NRM, MT, factor_team_kernel<NWv, MT, 0, MB, false>, factor_team_kernel<NWv, MT, 2, MB, false>, \
-                               factor_team_kernel<NWv, MT, 0, MB, true>, factor_team_kernel<NWv, MT, 2, MB, true>},
-static const TeamVariant g_team_variants[] = {TV(2, 14, 13, 1) TVF(3, 14, 7, 1) TV(4, 14, 5, 1)};
+struct TeamVariant { int nw, nrmax, maxt; factor_fn fn_d0, fn_d2; };
+#define TV(NWv, NRM, MT, MB) {NWv, NRM, MT, factor_team_kernel<NWv, MT, 0, MB>, factor_team_kernel<NWv, MT, 2, MB>},
+static const TeamVariant g_team_variants[] = {TV(2, 14, 13, 1) TV(3, 14, 7, 1) TV(4, 14, 5, 1)};
 #undef TV
-#undef TVF
 
 static int launch_factor_team(ccgp_ctx* ctx, FactorArgs& A, int* launched) {
     *launched = 0;
@@ -41,8 +36,7 @@ static int launch_factor_team(ccgp_ctx* ctx, FactorArgs& A, int* launched) {
     const size_t smem = tsm * TEAMS_PER_CTA + TEAM_CTA_EXTRA;
     if (smem > (size_t)ctx->max_smem_optin) return 0;
     const int threads = TEAMS_PER_CTA * var->nw * 32;
-    const bool fused = env_int("CCGP_TEAM_FUSED", 0) != 0 && var->fu_d0 != nullptr;   // measured slower (14.6 vs 16.8 M/s at n=100)
-    factor_fn fn = fused ? ((A.d == 2) ? var->fu_d2 : var->fu_d0) : ((A.d == 2) ? var->fn_d2 : var->fn_d0);
+    factor_fn fn = (A.d == 2) ? var->fn_d2 : var->fn_d0;
     CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int nb = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, threads, smem));
@@ -57,7 +51,7 @@ static int launch_factor_team(ccgp_ctx* ctx, FactorArgs& A, int* launched) {
     fn<<<(unsigned)grid, threads, smem, ctx->stream>>>(A);
     CK(cudaGetLastError());
     ctx->launches++;
-    ctx->last_team = var->nw * 32; ctx->last_smem = (int)smem; ctx->last_ctas = nb; ctx->last_variant = 400 + var->nw * 10 + (fused ? 1 : 0);
+    ctx->last_team = var->nw * 32; ctx->last_smem = (int)smem; ctx->last_ctas = nb; ctx->last_variant = 400 + var->nw * 10;
     *launched = 1;
     return 0;
 }
@@ -111,6 +105,10 @@ int launch_factor_mma(ccgp_ctx* ctx, FactorArgs& A, int* launched) {
     if ((kern == 0 && NR <= 14) || kern == 3) {
         RC(launch_factor_team(ctx, A, launched));
         if (*launched) return 0;
+        if (kern == 0) {                               // four teams no longer fit shared memory (n ~ 105..110): one warp each does
+            RC(launch_factor_warp(ctx, A, launched));
+            if (*launched) return 0;
+        }
     }
     if (l.npad < env_int("CCGP_MMA_MIN_NPAD", 40)) return 0;
     const int nw = env_int("CCGP_MMA_NW", 4);

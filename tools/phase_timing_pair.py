@@ -9,7 +9,7 @@ sys.path.insert(0, ROOT)
 import ccgp_b200  # noqa: E402
 from ccgp_b200 import workloads, GAUSS_ANISO_LAMBDA, LOGSCALE  # noqa: E402
 
-os.environ.setdefault("CCGP_KERNEL", "3"); os.environ.setdefault("CCGP_TEAM_NW", "2")
+os.environ.setdefault("CCGP_KERNEL", "3"); os.environ.setdefault("CCGP_TEAM_NW", "3")
 eng = ccgp_b200.Engine(0)
 X, y, s2 = workloads.m1_design()
 eng.set_design(X, y)
@@ -22,10 +22,10 @@ eng.nll_batch(th, GAUSS_ANISO_LAMBDA, s2, scale=LOGSCALE)
 eng._lib.ccgp_debug_phase_timing(eng._h, 0, C.cast(buf, C.c_void_p))
 print("variant", eng.last_nll_config())
 ncand = max(buf[15], 1)
-names = {0: ["top barrier", "build", "build barrier", "diag tile: last panel", "8x8 Cholesky + inverse + publish",
-             "step barrier (waits for B)", "-", "scalars + output"],
-         1: ["top barrier", "build", "build barrier", "last panel + lookahead (DMMA issue)", "wait for A's diagonal block",
-             "solve + store", "step barrier", "next parameters"]}
+names = {0: ["top barrier", "build", "build barrier", "8x8 Cholesky + inverse", "barrier with B (waits for the lookahead)",
+             "own solve of tile (c+1,c) + diagonal tile update", "-", "final barrier + scalars + output"],
+         1: ["top barrier", "build", "build barrier", "last panel + lookahead (DMMA issue)", "barrier with A (waits for the chain)",
+             "solve + store", "B-only barrier", "final barrier + next parameters"]}
 for w in (0, 1):
     tot = 0
     for ph, nm in enumerate(names[w]):
