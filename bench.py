@@ -120,7 +120,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": val, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # ------------------------------------------------------------------ clocks
@@ -180,7 +180,6 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "ERROR")      # keeps NCCL's version banner off stdout (one JSON line)
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     eng = ccgp_b200.Engine(local_rank)
     stream = torch.cuda.current_stream(dev)
@@ -346,15 +345,33 @@ def run_ours(args, rank, world, local_rank):
             "clocks": clocks,
             "me": me,
         }
-        print(json.dumps(line), flush=True)
+        _emit(line)
     eng.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_RESULT_FD = None
+
+
+def _emit(line):
+    """The one JSON line goes to the real stdout; everything else libraries print (NCCL's version banner,
+    warnings) was redirected to stderr for the duration of the run."""
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def main():
+    global _RESULT_FD
     args = parse()
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)          # keep the real stdout for the result line
+    os.dup2(2, 1)                   # anything else written to fd 1 (by C libraries too) lands on stderr
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -365,7 +382,7 @@ def main():
         # plain `python bench.py --gpus N`: re-launch under torchrun, one rank per GPU
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
                "--master-addr", "127.0.0.1", "--master-port", str(29400 + os.getpid() % 500)] + sys.argv
-        sys.exit(subprocess.call(cmd))
+        sys.exit(subprocess.call(cmd, stdout=_RESULT_FD))
     run_ours(args, rank, world, local_rank)
 
 
