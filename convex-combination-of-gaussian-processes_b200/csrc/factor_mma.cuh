@@ -209,8 +209,13 @@ __device__ __forceinline__ double2 mma_raw_tile(const FactorArgs& A, const doubl
 // additionally builds column j of inv(L) by forward substitution, interleaved with the factor
 // loop (row c of L is final when pivot c is taken, so x_c only waits for 1/L_cc).
 // `blk`: the tile (row-major, 64 doubles); `linv`: inv(L) row-major, 64 doubles.
-__device__ __forceinline__ void mma_diag(const FactorArgs& A, double* blk, double* linv, int c, int lane,
-                                         FactorResult& res) {
+// The determinant bookkeeping is redundant in every lane (the product of the tile's pivots, folded into
+// res.mant/es once per tile): res is valid in ALL lanes.  FULL: all 8 columns are design columns (no
+// per-column `live` selects).  The factor is written back only when `writeback` (the tile that holds
+// the rows y', 1' -- nobody else reads L_cc: the rows below are solved against its inverse).
+template <bool FULL>
+__device__ __forceinline__ void mma_diag_impl(const FactorArgs& A, double* blk, double* linv, int c, int lane,
+                                              FactorResult& res, bool writeback) {
     const int n = A.lay.n;
     double a[8][8];
 #pragma unroll
@@ -222,14 +227,14 @@ __device__ __forceinline__ void mma_diag(const FactorArgs& A, double* blk, doubl
         }
     const int jl = lane & 7;
     double x[8];
-    double pv_own = 1.0;
+    double pp = 1.0;                                      // product of the live pivots of this tile
+    int minhi = 0x7fffffff;                               // smallest high word among them (sign and size in one compare)
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         const double piv = a[k][k];
-        const bool live = (8 * c + k) < n;
+        const bool live = FULL || (8 * c + k) < n;
         const double ri = live ? fast_rsqrt(piv) : 0.0;
-        if (live && !(piv > PIVOT_MIN)) res.bad = 1;
-        if (live && lane == k + 8) pv_own = piv;
+        if (live) { pp *= piv; minhi = min(minhi, __double2hiint(piv)); }
         // inverse, row k: x_k = (e_k - sum_{q<k} L_kq x_q) / L_kk   (independent of ri until the last multiply)
         double s = (jl == k) ? 1.0 : 0.0;
 #pragma unroll
@@ -247,19 +252,43 @@ __device__ __forceinline__ void mma_diag(const FactorArgs& A, double* blk, doubl
 #pragma unroll
         for (int r = 0; r < 8; ++r) linv[r * 8 + lane] = x[r];
     }
-    if (lane == 8) {                            // one lane writes the factor back (upper part zeroed)
+    if (writeback && lane == 8) {               // one lane writes the factor back (upper part zeroed)
 #pragma unroll
         for (int r = 0; r < 8; ++r)
 #pragma unroll
             for (int k = 0; k <= r; k += 2) st2(blk + r * 8 + k, a[r][k], (k + 1 <= r) ? a[r][k + 1] : 0.0);
     }
-    if (lane >= 8 && lane < 16) {
-        prod_accum(res.mant_all, res.es_all, pv_own);
-        if (8 * c + (lane - 8) >= A.tail0) prod_accum(res.mant_tail, res.es_tail, pv_own);
+    // pivot <= PIVOT_MIN = 2^-46 (or negative, or NaN after an earlier bad pivot -- already flagged): high word test;
+    // a pivot of exactly 2^-46 with a non-zero low word passes, as in `piv > PIVOT_MIN`
+    if (minhi < 0x3d100000 || !(pp == pp)) res.bad = 1;   // (a NaN pivot makes the product NaN)
+    if (minhi == 0x3d100000) {                  // rare: decide the boundary binade exactly
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if ((FULL || (8 * c + k) < n) && !(a[k][k] * a[k][k] > PIVOT_MIN)) res.bad = 1;
+    }
+    prod_accum(res.mant_all, res.es_all, pp);
+    if (A.tail0 > 0) {                          // determinant of the trailing pivots only (ME criterion): rare path
+        if (8 * c >= A.tail0) {
+            prod_accum(res.mant_tail, res.es_tail, pp);
+        } else if (8 * c + 8 > A.tail0) {
+            double lt = 1.0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (8 * c + k >= A.tail0 && (FULL || (8 * c + k) < n)) lt *= a[k][k];       // L_kk = sqrt(pivot)
+            prod_accum(res.mant_tail, res.es_tail, lt * lt);
+        }
+    } else {
+        res.mant_tail = res.mant_all; res.es_tail = res.es_all;
     }
 }
+__device__ __forceinline__ void mma_diag(const FactorArgs& A, double* blk, double* linv, int c, int lane,
+                                         FactorResult& res) {
+    const int n = A.lay.n;
+    const bool writeback = (8 * c + 8 > n);     // the tile reaches the rows beyond the design (y', 1')
+    if (8 * c + 8 <= n) mma_diag_impl<true>(A, blk, linv, c, lane, res, writeback);
+    else mma_diag_impl<false>(A, blk, linv, c, lane, res, writeback);
+}
 
-// NW warps per candidate; MAXT = most tiles of one block column owned by one update warp
 // ---- update-warp pieces, specialised on the number NT of tiles the warp owns in the column ------
 // acc[t] -= L(r_t, J) L(rb, J)' for `npan` consecutive panels starting at the one `ap`/`bp` point
 // into (ap: this lane's slot of tile (r_0, J); bp: of tile (rb, J)); tiles r_t = r_0 + t NU.
@@ -474,19 +503,7 @@ __global__ void __launch_bounds__(NW * 32, 4) factor_mma_kernel(const FactorArgs
 
         // ---------------- scalars ----------------
         if (role == 0) {
-            res.bad = __any_sync(0xffffffffu, res.bad) ? 1 : 0;
-            double ma = 1.0, mt = 1.0;
-            int ea = 0, et = 0;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const double m1 = __shfl_sync(0xffffffffu, res.mant_all, 8 + k);
-                const double m2 = __shfl_sync(0xffffffffu, res.mant_tail, 8 + k);
-                const int e1 = __shfl_sync(0xffffffffu, res.es_all, 8 + k);
-                const int e2 = __shfl_sync(0xffffffffu, res.es_tail, 8 + k);
-                prod_accum(ma, ea, m1); ea += e1;
-                prod_accum(mt, et, m2); et += e2;
-            }
-            res.mant_all = ma; res.es_all = ea; res.mant_tail = mt; res.es_tail = et;
+            // res is valid in every lane of this warp (mma_diag keeps the bookkeeping redundantly)
         }
         if (A.out_mode == OUT_NLL) {
             double s11 = 0.0, s1y = 0.0;

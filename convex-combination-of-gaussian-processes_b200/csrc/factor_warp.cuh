@@ -187,19 +187,7 @@ __global__ void __launch_bounds__(WARP_TEAMS * 32, MINB) factor_warp_kernel(cons
 
         // ---------------- scalars ----------------
         {
-            res.bad = __any_sync(0xffffffffu, res.bad) ? 1 : 0;
-            double ma = 1.0, mt = 1.0;
-            int ea = 0, et = 0;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const double m1 = __shfl_sync(0xffffffffu, res.mant_all, 8 + k);
-                const double m2 = __shfl_sync(0xffffffffu, res.mant_tail, 8 + k);
-                const int e1 = __shfl_sync(0xffffffffu, res.es_all, 8 + k);
-                const int e2 = __shfl_sync(0xffffffffu, res.es_tail, 8 + k);
-                prod_accum(ma, ea, m1); ea += e1;
-                prod_accum(mt, et, m2); et += e2;
-            }
-            res.mant_all = ma; res.es_all = ea; res.mant_tail = mt; res.es_tail = et;
+            // res is valid in every lane of this warp (mma_diag keeps the bookkeeping redundantly)
         }
         if (A.out_mode == OUT_NLL) {
             double s11 = 0.0, s1y = 0.0;
