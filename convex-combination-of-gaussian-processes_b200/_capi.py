@@ -15,7 +15,7 @@ SYMBOLS = [
     "ccgp_nll_batch", "ccgp_nll_batch_dev", "ccgp_argmin_dev", "ccgp_nll_argmin", "ccgp_rinv_batch",
     "ccgp_predict", "ccgp_predict_dev", "ccgp_me_schur_batch", "ccgp_me_schur_batch_dev", "ccgp_me_argmin",
     "ccgp_subset_logdet_batch", "ccgp_subset_logdet_batch_dev", "ccgp_mixed_corr", "ccgp_debug_phase_timing",
-    "ccgp_kmedoids_pam", "ccgp_me_schur_paired",
+    "ccgp_kmedoids_pam", "ccgp_me_schur_paired", "ccgp_me_schur_stencil",
 ]
 
 _lib = None
@@ -70,6 +70,7 @@ def load():
     lib.ccgp_mixed_corr.argtypes = [vp, i32, dp, dp, i32, dp, i32, i32, dp]
     lib.ccgp_debug_phase_timing.argtypes = [vp, i32, vp]
     lib.ccgp_me_schur_paired.argtypes = [vp, dp, i32, i32, dp, i32, i64, dp, i64, i64, dp, ip]
+    lib.ccgp_me_schur_stencil.argtypes = [vp, dp, i32, i32, dp, i32, i64, dp, i64, i64, f64, f64, f64, dp, ip]
     lib.ccgp_kmedoids_pam.argtypes = [vp, dp, i64, i32, i32, i32, ip, dp, ip]
     for s in SYMBOLS:
         fn = getattr(lib, s)

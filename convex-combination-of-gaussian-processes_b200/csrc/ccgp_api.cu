@@ -715,6 +715,46 @@ extern "C" int ccgp_me_schur_paired(ccgp_ctx* ctx, const double* D_old, int n_ol
     return CCGP_OK;
 }
 
+// stencil form: K = P * group base designs (problem k belongs to parameter row k / group); the kernel evaluates each
+// at its 2m+1 central-difference points (m = n_new * d, step h, clipped to [lo, hi]) without the host ever
+// materialising them: out_vals[k * (2m+1) + s], s = 0 base, 1+2i: coordinate i + h, 2+2i: coordinate i - h
+extern "C" int ccgp_me_schur_stencil(ccgp_ctx* ctx, const double* D_old, int n_old, int d, const double* X, int n_new,
+                                     int64_t group, const double* params, int64_t P, int64_t ldq, double h, double lo,
+                                     double hi, double* out_vals, int32_t* out_status) {
+    if (!ctx) return CCGP_ERR_ARG;
+    ARG(n_old >= 0 && n_new >= 1 && d >= 1 && d <= MAXD && group >= 1 && P >= 0 && ldq >= P && h > 0 && lo < hi);
+    if (P == 0) return CCGP_OK;
+    ARG(X && params && out_vals);
+    ARG(n_old == 0 || D_old != nullptr);
+    if (!me_fast_supported(n_old, n_new, d)) {
+        snprintf(ctx->err, sizeof(ctx->err), "ccgp_me_schur_stencil: sizes beyond the ME kernel (n_new <= 8, n_old <= 32, d <= 4)");
+        return CCGP_ERR_UNSUPPORTED;
+    }
+    CK(cudaSetDevice(ctx->device));
+    const int m = n_new * d, S = 2 * m + 1;
+    const int64_t K = P * group, C = K * S;
+    size_t nold_d = (size_t)n_old * d, nnew = (size_t)K * m, npar = (size_t)P * 3, nout = (size_t)C;
+    size_t need = (nold_d + nnew + npar + nout) * 8 + nout * 4;
+    int rc = ensure_ws(ctx, need);
+    if (rc) return rc;
+    double* d_old = (double*)ctx->ws;
+    double* d_new = d_old + nold_d;
+    double* d_par = d_new + nnew;
+    double* d_neg = d_par + npar;
+    int32_t* d_st = (int32_t*)(d_neg + nout);
+    if (n_old) CK(cudaMemcpyAsync(d_old, D_old, nold_d * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_new, X, nnew * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpy2DAsync(d_par, (size_t)P * 8, params, (size_t)ldq * 8, (size_t)P * 8, 3, cudaMemcpyHostToDevice, ctx->stream));
+    rc = me_fast_launch(ctx->stream, ctx->num_sm, d_old, n_old, d, d_new, n_new, C, d_par, P, P, d_neg, nullptr, d_st,
+                        ctx->err, sizeof(ctx->err), group * S, S, h, lo, hi);
+    if (rc) return rc;
+    ctx->launches++;
+    CK(cudaMemcpyAsync(out_vals, d_neg, nout * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_status) CK(cudaMemcpyAsync(out_status, d_st, nout * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return CCGP_OK;
+}
+
 extern "C" int ccgp_me_argmin(ccgp_ctx* ctx, const double* D_old, int n_old, int d, const double* D_new, int n_new,
                               int64_t C, const double* params, int64_t P, int64_t ldq, double* best_val,
                               int64_t* best_idx) {

@@ -29,6 +29,9 @@ struct MeArgs {
     int64_t chunk;         // candidates per work item
     int64_t nchunks;       // ceil(candidates per parameter row / chunk)
     int64_t group;         // 0: every design x every parameter row; G > 0: designs [qG, (q+1)G) belong to row q (C = P G)
+    int stencil;           // S > 0: D_new holds C/S base designs; design c is base c/S with the central-difference
+                           // perturbation (c%S): 0 none, 1+2i: coordinate i + h, 2+2i: coordinate i - h (clipped to [lo, hi])
+    double h, lo, hi;
     double* negdet;        // C x P column-major (may be NULL)
     double* logdet;        // (may be NULL)
     int32_t* status;       // (may be NULL)
@@ -114,9 +117,14 @@ __global__ void __launch_bounds__(128) me_schur_kernel(const MeArgs M) {
             const bool valid = c < c_hi;
             const bool rowok = valid && r < n_new;
             double x[DM];
+            const int64_t cbase = M.stencil ? c / M.stencil : c;         // base design
+            const int sten = M.stencil ? (int)(c - cbase * M.stencil) : 0;
 #pragma unroll
-            for (int dd = 0; dd < DM; ++dd)
-                x[dd] = (rowok && dd < d) ? M.D_new[c * (int64_t)(n_new * d) + dd * n_new + r] : 0.0;
+            for (int dd = 0; dd < DM; ++dd) {
+                x[dd] = (rowok && dd < d) ? M.D_new[cbase * (int64_t)(n_new * d) + dd * n_new + r] : 0.0;
+                if (sten > 0 && ((sten - 1) >> 1) == dd * n_new + r)
+                    x[dd] = (sten & 1) ? fmin(x[dd] + M.h, M.hi) : fmax(x[dd] - M.h, M.lo);
+            }
             // cross correlations of new point r with the old design, then a = L_o^-1 (.)
             double a[NOLD];
 #pragma unroll
@@ -198,9 +206,9 @@ __global__ void __launch_bounds__(128) me_schur_kernel(const MeArgs M) {
 inline int me_fast_launch(cudaStream_t stream, int num_sm, const double* d_D_old, int n_old, int d,
                           const double* d_D_new, int n_new, int64_t C, const double* d_params, int64_t P,
                           int64_t ldq, double* d_negdet, double* d_logdet, int32_t* d_status, char* err, size_t errlen,
-                          int64_t group = 0) {
+                          int64_t group = 0, int stencil = 0, double h = 0.0, double lo = 0.0, double hi = 0.0) {
     MeArgs M;
-    M.group = group;
+    M.group = group; M.stencil = stencil; M.h = h; M.lo = lo; M.hi = hi;
     const int64_t Cq = group ? group : C;                  // candidates per parameter row
     M.D_old = d_D_old; M.D_new = d_D_new; M.params = d_params; M.ldq = ldq;
     M.n_old = n_old; M.n_new = n_new; M.d = d; M.C = C; M.P = P;

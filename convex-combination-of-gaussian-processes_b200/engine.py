@@ -245,6 +245,27 @@ class Engine:
                                                 _ptr(negdet), _ptr(status)))
         return negdet, status
 
+    def me_schur_stencil(self, D_old, X, n_new, d, params, group, h=1e-3, lower=-1.0, upper=1.0):
+        """X: (P*group, n_new*d) base designs as c(D) vectors -> vals[P*group, 2m+1] at the central-difference
+        stencil (column 0: base, 1+2i: coordinate i + h, 2+2i: coordinate i - h, clipped to the box), status."""
+        X = np.ascontiguousarray(np.asarray(X, dtype=np.float64))
+        params = _f(np.atleast_2d(params))
+        P = params.shape[0]
+        K, m = X.shape
+        if K != P * group or m != n_new * d:
+            raise ValueError("need P * group rows of n_new * d coordinates")
+        if D_old is None or len(D_old) == 0:
+            Do, n_old = None, 0
+        else:
+            Do = _f(np.atleast_2d(D_old))
+            n_old = Do.shape[0]
+        S = 2 * m + 1
+        vals = np.empty((K, S))
+        status = np.empty((K, S), dtype=np.int32)
+        self._ck(self._lib.ccgp_me_schur_stencil(self._h, _ptr(Do), n_old, d, _ptr(X), n_new, int(group), _ptr(params), P, P,
+                                                 float(h), float(lower), float(upper), _ptr(vals), _ptr(status)))
+        return vals, status
+
     def kmedoids_pam(self, P, k, max_swaps=1000):
         """PAM k-medoids of the rows of P (Euclidean) -> (medoid row indices[k], total cost, swaps)."""
         P = _f(np.atleast_2d(P))

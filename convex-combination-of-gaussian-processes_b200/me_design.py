@@ -7,8 +7,8 @@ of parameters drawn from the posterior" (reference ReadMe.md:54-56): `Batch.Entr
 reference does this one `optim` call at a time (and the driving script is not shipped).
 
 Here all (draw, start) problems advance together: one iteration = ONE paired batch of Schur
-determinants for the gradients (K problems x 28 stencil points, `ccgp_me_schur_paired`) plus one
-per line-search trial.  The optimiser is a bound-projected L-BFGS (two-loop recursion, memory 5,
+determinants for the gradients (K problems x 28 stencil points generated on the device,
+`ccgp_me_schur_stencil`) plus one per line-search trial (`ccgp_me_schur_paired`).  The optimiser is a bound-projected L-BFGS (two-loop recursion, memory 5,
 Armijo backtracking on the projected step, variables pinned at a bound whose gradient points
 outward are frozen): same problem class and stopping rule as optim's L-BFGS-B (factr = 1e7,
 pgtol = 0, maxit = 100, central differences with ndeps = 1e-3), not a transcription of lbfgsb.c --
@@ -19,10 +19,14 @@ from __future__ import annotations
 import numpy as np
 
 
-def lockstep_minimize(fun_batch, X0, lower, upper, maxit=100, factr=1e7, ndeps=1e-3, memory=5, max_backtrack=12):
+def lockstep_minimize(fun_batch, X0, lower, upper, maxit=100, factr=1e7, ndeps=1e-3, memory=5, max_backtrack=12,
+                      stencil_batch=None):
     """Minimise K independent box-constrained problems in lock-step.
     fun_batch(X[B, m], owner[B]) -> f[B]: objective of problem owner[b] at X[b] (owner is sorted, every problem
-    appears the same number of times in one call).  -> dict(x[K,m], f[K], iterations, evals, converged[K])."""
+    appears the same number of times in one call).  stencil_batch(X[K, m]) -> vals[K, 2m+1], optional: the
+    objective at the central-difference points of every row (column 0: the row itself, 1+2i / 2+2i: coordinate i
+    plus / minus ndeps, clipped to the box), produced without materialising them on the host.
+    -> dict(x[K,m], f[K], iterations, evals, converged[K])."""
     X = np.clip(np.asarray(X0, dtype=np.float64), lower, upper)
     K, m = X.shape
     ids = np.arange(K)
@@ -35,6 +39,13 @@ def lockstep_minimize(fun_batch, X0, lower, upper, maxit=100, factr=1e7, ndeps=1
         return np.where(np.isfinite(v), v, np.inf)
 
     def grad(Xc):
+        nonlocal evals
+        if stencil_batch is not None:
+            vals = np.asarray(stencil_batch(Xc), dtype=np.float64)
+            evals += vals.size
+            vals = np.where(np.isfinite(vals), vals, np.inf)
+            eps = np.minimum(Xc + ndeps, upper) - np.maximum(Xc - ndeps, lower)
+            return (vals[:, 1::2] - vals[:, 2::2]) / eps
         # central differences, the step shrunk at a bound exactly as optim does not: R's fmingr evaluates
         # outside-the-box points clipped to the bound with the epsilon adjusted -- we do the same
         Xp = np.repeat(Xc[:, None, :], m, axis=1)
@@ -126,7 +137,7 @@ def random_lhd_starts(rng, count, n_new, d):
     return out
 
 
-def all_subdesigns(D_old, params, n_new, d, n_starts, rng, engine, maxit=100, starts=None):
+def all_subdesigns(D_old, params, n_new, d, n_starts, rng, engine, maxit=100, starts=None, device_stencil=True):
     """One `Batch.Entropy.optim` ([M]:920-948) per parameter row (p, theta1, theta2), all rows and all starts in
     lock-step.  -> dict(designs[P, n_new, d] (the All_Subdesigns array), values[P] (= -det, the minimised
     criterion), all_values[P, n_starts], iterations, evals)."""
@@ -142,7 +153,10 @@ def all_subdesigns(D_old, params, n_new, d, n_starts, rng, engine, maxit=100, st
         designs = Xb.reshape(-1, d, n_new).transpose(0, 2, 1)
         return engine.me_schur_paired(D_old, designs, params, group)[0]
 
-    res = lockstep_minimize(fun, X0, -1.0, 1.0, maxit=maxit)
+    def stencil(Xc):                                        # the 2m+1 points of every problem, generated on the device
+        return engine.me_schur_stencil(D_old, Xc, n_new, d, params, n_starts, h=1e-3, lower=-1.0, upper=1.0)[0]
+
+    res = lockstep_minimize(fun, X0, -1.0, 1.0, maxit=maxit, stencil_batch=stencil if device_stencil else None)
     fv = res["f"].reshape(P, n_starts)
     best = np.argmin(fv, axis=1)                             # which.min over the starts ([M]:944)
     xs = res["x"].reshape(P, n_starts, n_new * d)[np.arange(P), best]

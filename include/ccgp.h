@@ -155,6 +155,16 @@ int ccgp_me_schur_paired(ccgp_ctx* ctx, const double* D_old, int n_old, int d,
                          const double* D_new, int n_new, int64_t group,
                          const double* params, int64_t P, int64_t ldq,
                          double* out_negdet, int32_t* out_status);
+/* Stencil form for the finite-difference gradients of optim's L-BFGS-B inside Batch.Entropy.optim ([M]:936):
+ * X holds K = P * group base designs as c(D.new) vectors (n_new*d doubles each, problem k -> parameter row
+ * k / group); every one is evaluated at its 2m+1 central-difference points (m = n_new*d, step h, clipped
+ * to [lo, hi]) generated on the device.  out_vals[k*(2m+1) + s]: s = 0 base, 1+2i: coordinate i + h,
+ * 2+2i: coordinate i - h. */
+int ccgp_me_schur_stencil(ccgp_ctx* ctx, const double* D_old, int n_old, int d,
+                          const double* X, int n_new, int64_t group,
+                          const double* params, int64_t P, int64_t ldq,
+                          double h, double lo, double hi,
+                          double* out_vals, int32_t* out_status);
 /* which.min over the candidates of each parameter row ([M]:944-945):
  * best_idx[q] = first c minimising out_negdet[c,q], best_val[q] its value. */
 int ccgp_me_argmin(ccgp_ctx* ctx, const double* D_old, int n_old, int d,

@@ -168,3 +168,19 @@ SEXP ccgp_R_me_schur_paired(SEXP ptr, SEXP D_old, SEXP D_new, SEXP n_new_, SEXP 
     check(ctx, rc, "me_schur_paired");
     return out;
 }
+
+/* Central-difference stencil of the ME criterion, generated on the device: X is (n_new*d) x (P*group) (columns =
+ * c(D.new) of each problem).  Returns the (2m+1) x (P*group) matrix of criterion values (row 1: base point). */
+SEXP ccgp_R_me_schur_stencil(SEXP ptr, SEXP D_old, SEXP X, SEXP n_new_, SEXP d_, SEXP params, SEXP group_, SEXP h_, SEXP lo_, SEXP hi_) {
+    ccgp_ctx* ctx = get_ctx(ptr);
+    int n_new = Rf_asInteger(n_new_), d = Rf_asInteger(d_);
+    int n_old = Rf_isNull(D_old) ? 0 : Rf_nrows(D_old);
+    int64_t K = Rf_ncols(X), P = Rf_nrows(params), group = Rf_asInteger(group_);
+    if (K != P * group) Rf_error("ccgp: need nrow(params) * group problems");
+    SEXP vals = PROTECT(Rf_allocMatrix(REALSXP, 2 * n_new * d + 1, (int)K));
+    int rc = ccgp_me_schur_stencil(ctx, n_old ? REAL(D_old) : NULL, n_old, d, REAL(X), n_new, group, REAL(params), P, P,
+                                   Rf_asReal(h_), Rf_asReal(lo_), Rf_asReal(hi_), REAL(vals), NULL);
+    UNPROTECT(1);
+    check(ctx, rc, "me_schur_stencil");
+    return vals;
+}

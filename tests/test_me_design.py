@@ -55,6 +55,28 @@ def test_gpu_paired_matches_cross_product_and_oracle(engine, designs):
 
 
 @pytest.mark.gpu
+def test_gpu_device_stencil_equals_explicit_designs(engine, designs):
+    D_old = designs["me_initial14"]
+    rng = np.random.default_rng(3)
+    params = np.array([[0.5, 1.0, 4.0], [0.3, 2.0, 3.0]])
+    X = me_design.random_lhd_starts(rng, 2 * 3, 7, 2)
+    X[0, 5] = 1.0                                          # on the upper bound: the + point is clipped
+    X[4, 9] = -0.9995                                      # within h of the lower bound
+    vals, st = engine.me_schur_stencil(D_old, X, 7, 2, params, 3, h=1e-3, lower=-1.0, upper=1.0)
+    assert vals.shape == (6, 29) and np.all(st == 0)
+    pts = np.repeat(X[:, None, :], 29, axis=1)
+    for i in range(14):
+        pts[:, 1 + 2 * i, i] = np.minimum(X[:, i] + 1e-3, 1.0)
+        pts[:, 2 + 2 * i, i] = np.maximum(X[:, i] - 1e-3, -1.0)
+    want = engine.me_schur_paired(D_old, pts.reshape(-1, 2, 7).transpose(0, 2, 1), params, 3 * 29)[0].reshape(6, 29)
+    np.testing.assert_array_equal(vals, want)
+    a = me_design.all_subdesigns(D_old, params, 7, 2, 3, rng, engine, starts=X, maxit=30, device_stencil=True)
+    b = me_design.all_subdesigns(D_old, params, 7, 2, 3, rng, engine, starts=X, maxit=30, device_stencil=False)
+    np.testing.assert_array_equal(a["designs"], b["designs"])
+    np.testing.assert_array_equal(a["all_values"], b["all_values"])
+
+
+@pytest.mark.gpu
 def test_gpu_all_subdesigns_lockstep_vs_sequential_optim(engine, designs):
     from ccgp_b200 import reference_api as api
     D_old = designs["me_initial14"]
