@@ -42,7 +42,8 @@ inline bool me_fast_supported(int n_old, int n_new, int d) {
 }
 
 // NOLD: rows of the old design the kernel is unrolled for; DM: coordinates it is unrolled for (d <= DM)
-template <int NOLD, int DM>
+// STENCIL: designs are generated from base designs (central-difference points), see MeArgs::stencil
+template <int NOLD, int DM, bool STENCIL>
 __global__ void __launch_bounds__(128) me_schur_kernel(const MeArgs M) {
     __shared__ double Lo[NOLD * NOLD];        // L_old, row-major Lo[j*NOLD + k], k <= j
     __shared__ double rio[NOLD];              // 1 / L_old(j,j)
@@ -117,12 +118,12 @@ __global__ void __launch_bounds__(128) me_schur_kernel(const MeArgs M) {
             const bool valid = c < c_hi;
             const bool rowok = valid && r < n_new;
             double x[DM];
-            const int64_t cbase = M.stencil ? c / M.stencil : c;         // base design
-            const int sten = M.stencil ? (int)(c - cbase * M.stencil) : 0;
+            const int64_t cbase = STENCIL ? c / M.stencil : c;           // base design
+            const int sten = STENCIL ? (int)(c - cbase * M.stencil) : 0;
 #pragma unroll
             for (int dd = 0; dd < DM; ++dd) {
                 x[dd] = (rowok && dd < d) ? M.D_new[cbase * (int64_t)(n_new * d) + dd * n_new + r] : 0.0;
-                if (sten > 0 && ((sten - 1) >> 1) == dd * n_new + r)
+                if (STENCIL && sten > 0 && ((sten - 1) >> 1) == dd * n_new + r)
                     x[dd] = (sten & 1) ? fmin(x[dd] + M.h, M.hi) : fmax(x[dd] - M.h, M.lo);
             }
             // cross correlations of new point r with the old design, then a = L_o^-1 (.)
@@ -222,8 +223,10 @@ inline int me_fast_launch(cudaStream_t stream, int num_sm, const double* d_D_old
     const int64_t items = P * M.nchunks;
     const int grid = (int)std::min<int64_t>(items, (int64_t)num_sm * 8);
     // 14 = the reference's initial design ([M]:980); d = 2 in the shipped script
-#define CCGP_ME_LAUNCH(NO) do { if (d <= 2) me_schur_kernel<NO, 2><<<grid, 128, 0, stream>>>(M); \
-                                else me_schur_kernel<NO, 4><<<grid, 128, 0, stream>>>(M); } while (0)
+#define CCGP_ME_LAUNCH(NO) do { if (stencil) { if (d <= 2) me_schur_kernel<NO, 2, true><<<grid, 128, 0, stream>>>(M); \
+                                               else me_schur_kernel<NO, 4, true><<<grid, 128, 0, stream>>>(M); } \
+                                else if (d <= 2) me_schur_kernel<NO, 2, false><<<grid, 128, 0, stream>>>(M); \
+                                else me_schur_kernel<NO, 4, false><<<grid, 128, 0, stream>>>(M); } while (0)
     if (n_old <= 8) CCGP_ME_LAUNCH(8);
     else if (n_old <= 14) CCGP_ME_LAUNCH(14);
     else if (n_old <= 16) CCGP_ME_LAUNCH(16);
