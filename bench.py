@@ -330,7 +330,7 @@ def run_ours(args, rank, world, local_rank):
                              % ((B * BYTES_PER_EVAL) >> 20),
                        "kernel": cfg, "not_pd_candidates": n_bad,
                        "argmin": {"nll": gmin[0], "index": gmin[1]}},
-            "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak / 1e12, "unit": "TFLOP/s",
+            "roofline": {"bound": "tensor", "bound_detail": "FP64 pipe: DFMA and the FP64 tensor form (mma.sync.m8n8k4.f64, DMMA) share it at 64 FMA/clk/SM; tcgen05 has no FP64 kind", "achieved": achieved_tf, "peak": peak / 1e12, "unit": "TFLOP/s",
                          "frac": achieved_tf / (peak / 1e12),
                          "peak_source": "measured live: dependent-free DFMA loop on all SMs (MEASURED_PEAKS.json has no FP64 entry)",
                          "flop_per_eval": FLOP_PER_EVAL, "exp_per_eval": EXP_PER_EVAL,
