@@ -162,7 +162,17 @@ def choose_hyperpars(D_train, y_train, hyperpars_matrix, sigma2, N=1728, tau=100
     eng.set_design(D_train, y_train)
     hp = np.atleast_2d(hyperpars_matrix)
     H = hp.shape[0]
-    cand = np.vstack([sweep_candidates(hp[i, 0:2], hp[i, 2:4], N) for i in range(H)])
+    # qigamma(u, a, b) = b / qgamma(1 - u, a): the quantile function is needed once per distinct SHAPE only
+    # (the grids hold a handful of shapes), the scale is a multiplication -- same numbers as sweep_candidates
+    from scipy.stats import gamma
+    u = halton_base2(N)
+    qg = {a: gamma.ppf(1.0 - u, a=a) for a in np.unique(hp[:, [0, 2]])}
+    cand = np.empty((H * N, 3))
+    for i in range(H):
+        blk = cand[i * N:(i + 1) * N]
+        blk[:, 0] = u
+        blk[:, 1] = 1.0 / (qg[hp[i, 0]] * (1.0 / hp[i, 1]))
+        blk[:, 2] = 1.0 / (qg[hp[i, 2]] * (1.0 / hp[i, 3]))
     nll, _, _ = eng.nll_batch(cand, GAUSS_ISO, sigma2, mean_mode=MEAN_ZERO_PLUS_TAU2, tau=tau)
     likes = np.exp(-nll).reshape(H, N).mean(axis=1)
     if take_log:
