@@ -12,6 +12,7 @@
 #include "../../include/ccgp.h"
 #include "ccgp_ctx.h"
 #include "predict_kernel.cuh"
+#include "predict_mma.cuh"
 #include "me_kernel.cuh"
 #include "bigchol.cuh"
 
@@ -572,6 +573,29 @@ extern "C" int ccgp_predict_dev(ccgp_ctx* ctx, int family, const double* d_pars,
     P.vec_unnormalised = (family == CCGP_MATERN_SPLINE1D && !env_int("CCGP_NO_Q3", 0)) ? 1 : 0;
     P.out_mean = d_mean; P.out_var = d_var; P.status = d_status;
     const int n = ctx->n;
+    // Gaussian families: the tensor-path kernel (predict_mma.cuh) while its factor + site buffers fit shared memory
+    if (family < CCGP_MATERN1D && (d_pars_vec == nullptr || vec_family < CCGP_MATERN1D) && !env_int("CCGP_PREDICT_OLD", 0)) {
+        const Layout& l = A.lay;
+        const int NR = l.npad / 8;
+        const size_t smem = predict_mma_smem_bytes(l, A.d);
+        typedef void (*pfn)(const PredictArgs);
+        pfn fn = nullptr;
+        if (NR <= 7) fn = (A.d == 2) ? predict_mma_kernel<2, 2> : predict_mma_kernel<2, 0>;
+        else if (NR <= 13) fn = (A.d == 2) ? predict_mma_kernel<4, 2> : predict_mma_kernel<4, 0>;
+        else if (NR <= 16) fn = (A.d == 2) ? predict_mma_kernel<5, 2> : predict_mma_kernel<5, 0>;
+        if (fn && smem <= (size_t)ctx->max_smem_optin) {
+            CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int nb = 0;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, PM_NW * 32, smem));
+            if (nb >= 1) {
+                const int64_t grid = std::min<int64_t>(S, (int64_t)nb * ctx->num_sm);
+                fn<<<(unsigned)grid, PM_NW * 32, smem, ctx->stream>>>(P);
+                CK(cudaGetLastError());
+                ctx->launches++;
+                return CCGP_OK;
+            }
+        }
+    }
     if (n <= 32) return launch_predict<64, 4, 4, 1, 8>(ctx, P);
     if (n <= 64) return launch_predict<128, 4, 4, 2, 4>(ctx, P);
     if (n <= 128) return launch_predict<128, 4, 4, 4, 4>(ctx, P);

@@ -503,3 +503,45 @@ def test_determinant_mode_on_every_dmma_kernel(engine, golden, designs):
             assert np.array_equal(np.argmin(nd, axis=0), np.argmin(base_me, axis=0)), name
     finally:
         os.environ.pop("CCGP_ME_GENERIC", None)
+
+
+@pytest.mark.parametrize("n,d,family,T", [(14, 2, GAUSS_ANISO_LAMBDA, 37), (47, 3, GAUSS_ISO, 16), (64, 4, GAUSS_ISO, 14),
+                                          (100, 2, GAUSS_ANISO_LAMBDA, 625), (110, 2, GAUSS_ISO_RAW2, 51), (126, 2, GAUSS_ISO, 9)])
+def test_predict_tensor_path_matches_substitution_kernel_and_oracle(engine, n, d, family, T):
+    """The tensor-path predictive table (sites as extra rows of the factorisation) against the lane-distributed
+    substitution kernel (CCGP_PREDICT_OLD=1) and, on a few entries, the oracle's predict.post."""
+    rng = np.random.default_rng(900 + n)
+    X = rng.uniform(-1, 1, (n, d))
+    y = np.sin(2 * X[:, 0]) + 0.1 * rng.normal(size=n)
+    S = 7
+    scale = 3.0 * n ** (1.0 / d)
+    if family == GAUSS_ANISO_LAMBDA:
+        pars = np.column_stack([rng.uniform(0.1, 0.9, S)] + [scale * rng.uniform(1, 3, S) for _ in range(d)] + [rng.uniform(0.3, 2, S)])
+        of = orc.FAMILY_ANISO_LAMBDA
+    else:
+        pars = np.column_stack([rng.uniform(0.1, 0.9, S), scale * rng.uniform(1, 3, S), scale * rng.uniform(2, 6, S)])
+        of = orc.FAMILY_ISO if family == GAUSS_ISO else orc.FAMILY_ISO_RAW2
+    pars[3, 1:] *= 1e-19                                   # singular row: NaN column, status 1 on both paths
+    Xn = np.vstack([rng.uniform(-1.2, 1.2, (T - 1, d)), X[:1]])     # the last site is a design point
+    engine.set_design(X, y)
+    pv = None
+    vf = -1
+    if family == GAUSS_ISO_RAW2:                           # quirk Q2: the vector uses theta1 * (1 + lambda)
+        pv = np.column_stack([pars[:, 0], pars[:, 1], pars[:, 1] * (1.0 + pars[:, 2])])
+        vf = GAUSS_ISO
+    new = engine.predict(pars, family, Xn, 2.5, pars_vec=pv, vec_family=vf)
+    os.environ["CCGP_PREDICT_OLD"] = "1"
+    try:
+        old = engine.predict(pars, family, Xn, 2.5, pars_vec=pv, vec_family=vf)
+    finally:
+        os.environ.pop("CCGP_PREDICT_OLD", None)
+    assert np.array_equal(new[2], old[2]) and new[2][3] == 1
+    ok = new[2] == 0
+    assert np.isnan(new[0][:, 3]).all() and np.isnan(new[1][:, 3]).all()
+    assert rel_err(new[0][:, ok], old[0][:, ok]).max() < TOL
+    assert np.abs(new[1][:, ok] - old[1][:, ok]).max() < 1e-9 * 2.5
+    if family != GAUSS_ISO_RAW2:                           # (with quirk Q2 the vector is not a column of the matrix: no interpolation)
+        assert np.abs(new[0][-1, ok] - y[0]).max() < 1e-7 and np.abs(new[1][-1, ok]).max() < 1e-7     # a design point is reproduced
+        tab = orc.predict_table(X, y, 2.5, of, pars[:2], Xn[:5])
+        assert rel_err(new[0][:5, :2], tab[0]).max() < TOL
+        assert np.abs(new[1][:5, :2] - tab[1]).max() < 1e-9 * 2.5
