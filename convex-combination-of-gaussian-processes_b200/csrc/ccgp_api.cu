@@ -252,6 +252,17 @@ extern "C" int ccgp_set_design(ccgp_ctx* ctx, const double* X, int n, int d, con
     return CCGP_OK;
 }
 
+// copy stream + events of the chunk-pipelined host-pointer entry points
+static int ensure_copy_stream(ccgp_ctx* ctx) {
+    if (ctx->copy_stream) return 0;
+    CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        CK(cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ctx->ev_kern[i], cudaEventDisableTiming));
+    }
+    return 0;
+}
+
 // ------------------------------------------------------------------ NLL
 static int check_nll_args(ccgp_ctx* ctx, int family, int scale, const void* cand, int64_t B, int64_t ldc,
                           double sigma2, int mean_mode) {
@@ -332,13 +343,7 @@ extern "C" int ccgp_nll_batch(ccgp_ctx* ctx, int family, int scale, const double
     // the calling thread, not the GPU.  Small batches go through in one piece.
     int64_t nchunk = env_int("CCGP_H2D_CHUNKS", 0);
     if (nchunk <= 0) nchunk = (B >= (1 << 16)) ? 8 : 1;
-    if (!ctx->copy_stream) {
-        CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-        for (int i = 0; i < 2; ++i) {
-            CK(cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming));
-            CK(cudaEventCreateWithFlags(&ctx->ev_kern[i], cudaEventDisableTiming));
-        }
-    }
+    RC(ensure_copy_stream(ctx));
     const int64_t step = (B + nchunk - 1) / nchunk;
     auto fetch = [&](int64_t b0, int64_t nb) -> int {       // results of rows [b0, b0+nb) -> host, after their kernel
         CK(cudaMemcpyAsync(out_nll + b0, d_nll + b0, (size_t)nb * 8, cudaMemcpyDeviceToHost, ctx->copy_stream));
@@ -629,11 +634,34 @@ extern "C" int ccgp_predict(ccgp_ctx* ctx, int family, const double* pars, int64
     CK(cudaMemcpy2DAsync(d_pars, (size_t)S * 8, pars, (size_t)ldp * 8, (size_t)S * 8, k, cudaMemcpyHostToDevice, ctx->stream));
     if (pars_vec) CK(cudaMemcpy2DAsync(d_pv, (size_t)S * 8, pars_vec, (size_t)ldpv * 8, (size_t)S * 8, kv, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(d_xn, Xnew, (size_t)T * d * 8, cudaMemcpyHostToDevice, ctx->stream));
-    rc = ccgp_predict_dev(ctx, family, d_pars, S, S, vec_family, pars_vec ? d_pv : nullptr, S, d_xn, T, sigma2, d_mean, d_var, d_status);
-    if (rc) return rc;
-    CK(cudaMemcpyAsync(out_mean, d_mean, (size_t)T * S * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(out_var, d_var, (size_t)T * S * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    if (out_status) CK(cudaMemcpyAsync(out_status, d_status, (size_t)S * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    // posterior rows in chunks: the table of chunk i travels back (copy stream) while chunk i+1 is computed
+    int64_t nchunk = env_int("CCGP_PREDICT_CHUNKS", 0);
+    if (nchunk <= 0) nchunk = ((double)S * (double)T >= 131072.0 && S >= 64) ? 4 : 1;
+    RC(ensure_copy_stream(ctx));
+    const int64_t step = (S + nchunk - 1) / nchunk;
+    auto fetch = [&](int64_t s0, int64_t ns) -> int {       // (copies to pageable memory block the caller, not the GPU)
+        CK(cudaMemcpyAsync(out_mean + (size_t)T * s0, d_mean + (size_t)T * s0, (size_t)T * ns * 8, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        CK(cudaMemcpyAsync(out_var + (size_t)T * s0, d_var + (size_t)T * s0, (size_t)T * ns * 8, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        return 0;
+    };
+    int slot = 0;
+    int64_t prev_s0 = -1, prev_ns = 0;
+    for (int64_t s0 = 0; s0 < S; s0 += step, slot ^= 1) {
+        const int64_t ns = std::min(step, S - s0);
+        rc = ccgp_predict_dev(ctx, family, d_pars + s0, ns, S, vec_family, pars_vec ? d_pv + s0 : nullptr, S, d_xn, T, sigma2,
+                              d_mean + (size_t)T * s0, d_var + (size_t)T * s0, d_status + s0);
+        if (rc) return rc;
+        CK(cudaEventRecord(ctx->ev_kern[slot], ctx->stream));
+        if (prev_s0 >= 0) {                                  // the previous chunk's table travels while this chunk is computed
+            CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_kern[slot ^ 1], 0));
+            if ((rc = fetch(prev_s0, prev_ns))) return rc;
+        }
+        prev_s0 = s0; prev_ns = ns;
+    }
+    CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_kern[slot ^ 1], 0));
+    if ((rc = fetch(prev_s0, prev_ns))) return rc;
+    if (out_status) CK(cudaMemcpyAsync(out_status, d_status, (size_t)S * 4, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    CK(cudaStreamSynchronize(ctx->copy_stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return CCGP_OK;
 }
