@@ -254,6 +254,7 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- M2: ME subset (Schur) determinants/sec, pool(1000) x params(1000) per step, resident inputs
     me = None
+    pred = None
     if not args.no_me:
         eng.set_stream(stream.cuda_stream)
         D_old, pool = workloads.me_pool()
@@ -281,6 +282,36 @@ def run_ours(args, rank, world, local_rank):
         me = {"metric": "ME subset (Schur) log-dets/sec", "value": world * 1000 * P * me_steps / (me_ms * 1e-3),
               "unit": "dets/s", "workload": "ME-A: Initial ME Design (14x2) + 1000 All_Subdesigns blocks x 1000 parameter rows per GPU per step",
               "ms_per_step": me_ms / me_steps}
+        # ---- predictive table (the prediction() stage of the same fit): S posterior rows x T = 625 grid sites, n = 100
+        S_p, T_p = 1000, 625
+        rng_p = np.random.default_rng(4242 + rank)
+        pars_p = workloads.m1_candidates(S_p, seed=99 + rank)
+        nat_p = np.column_stack([1.0 / (1.0 + np.exp(-pars_p[:, 2])), np.exp(pars_p[:, 0]), np.exp(pars_p[:, 1]), np.exp(pars_p[:, 3])])
+        gx = np.linspace(-1.0, 1.0, 25)
+        Xn = np.array([(a, b) for a in gx for b in gx])                       # the 25 x 25 grid of [A]:851-853
+        d_pp = torch.from_numpy(np.asfortranarray(nat_p).T.copy()).to(dev)
+        d_xn = torch.from_numpy(np.asfortranarray(Xn).T.copy()).to(dev)
+        pm = torch.empty(S_p * T_p, dtype=torch.float64, device=dev)
+        pvv = torch.empty(S_p * T_p, dtype=torch.float64, device=dev)
+        for _ in range(3):
+            eng.predict_dev(d_pp, GAUSS_ANISO_LAMBDA, d_xn, s2, pm, pvv)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(me_steps):
+            eng.predict_dev(d_pp, GAUSS_ANISO_LAMBDA, d_xn, s2, pm, pvv)
+        e1.record(stream)
+        barrier()
+        p_ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([p_ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            p_ms = float(t.item())
+        pflop = S_p * T_p * (100 * (3 * 2 + 4) + 2.0 * 100 * 100 + 6 * 100) + S_p * 100 ** 3 / 3.0
+        pred = {"metric": "predictive (posterior row, site) pairs/sec", "value": world * S_p * T_p * me_steps / (p_ms * 1e-3),
+                "unit": "pairs/s", "workload": "n=100 d=2 anisotropic, S=1000 posterior rows x T=625 (25x25 grid) per GPU per step",
+                "ms_per_step": p_ms / me_steps, "tflops_algorithmic": pflop * me_steps / (p_ms * 1e-3) / 1e12,
+                "finite": bool(torch.isfinite(pm).all().item())}
         eng.set_stream(None)
 
     # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload
@@ -343,7 +374,7 @@ def run_ours(args, rank, world, local_rank):
                     "d2h_bytes_per_step": int(B * 20), "timed": "wall clock around %d synchronous ccgp_nll_batch host calls" % ksteps},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "me": me,
+            "me": me, "predict": pred,
         }
         _emit(line)
     eng.close()

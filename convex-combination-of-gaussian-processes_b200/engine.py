@@ -193,6 +193,14 @@ class Engine:
                                                _ptr(negdet), _ptr(logdet), _ptr(status)))
         return negdet, logdet, status
 
+    def predict_dev(self, pars_t, family, Xnew_t, sigma2, out_mean, out_var, out_status=None):
+        """torch CUDA tensors: pars_t k x S row-major (= S x k column-major), Xnew_t d x T row-major; out_* T*S. Async."""
+        k, S = pars_t.shape
+        d, T = Xnew_t.shape
+        self._ck(self._lib.ccgp_predict_dev(self._h, family, pars_t.data_ptr(), S, S, -1, None, S, Xnew_t.data_ptr(), T,
+                                            float(sigma2), out_mean.data_ptr(), out_var.data_ptr(),
+                                            out_status.data_ptr() if out_status is not None else None))
+
     def me_schur_batch_dev(self, D_old_t, n_old, d, D_new_t, n_new, Cn, params_t, P, out_negdet, out_logdet=None, out_status=None):
         self._ck(self._lib.ccgp_me_schur_batch_dev(
             self._h, D_old_t.data_ptr() if D_old_t is not None else None, n_old, d, D_new_t.data_ptr(), n_new, Cn,
