@@ -12,8 +12,11 @@ the R functions line by line, using the same LAPACK routines base R calls
 (dgesv+dgecon for `solve`, dgetrf for `det`, dpotrf/dpotri for `chol`/
 `chol2inv`), and is cross-checked three ways in tests/: reference-faithful path
 vs minimal (Cholesky) path vs a 50-digit mpmath truth.
-One piece IS pinned by shipped files: `pam_kmedoids` reproduces rows 15-21 of
-`k-medoids ME Design.txt` from `All_Subdesigns.txt` exactly (tests/test_kmedoids.py).
+Two pieces ARE pinned by shipped files: `pam_kmedoids` reproduces rows 15-21 of
+`k-medoids ME Design.txt` from `All_Subdesigns.txt` exactly (tests/test_kmedoids.py); and the
+likelihood + predictor, driven through the Metropolis loop, reproduce the reference's only
+stored output (`Ground Vibrations Emulator/Results/Size 50 Results 1.txt`) statistically:
+RMSPE and the predictions themselves (tests/test_end_to_end_gv.py; their chain is unseeded).
 
 File aliases (all under /root/reference):
   [A] 2D Codes and Designs/2D Combined GP Anisotropic Public.R

@@ -39,3 +39,28 @@ def test_gpu_fit_reproduces_the_stored_ground_vibrations_result(engine, stored):
     assert rm(r["yhat"], stored["y_hat_combined"]) < 0.3                        # measured 0.10 (sd of y.true: 3.24)
     assert np.corrcoef(r["yhat"], stored["y_hat_combined"])[0, 1] > 0.995
     assert r["samples"] == 32 * 1000 and r["accepted"] >= 32 * 1000
+
+
+def test_oracle_fit_reproduces_the_stored_result_statistically(stored, designs):
+    """The same pipeline with the CPU oracle as the likelihood and predictor: pins the oracle itself (statistically) to
+    the reference's stored output, independent of the CUDA library."""
+    from oracle import ccgp_oracle as orc
+    from ccgp_b200 import samplers
+    tr, te = designs["gv50_train1"], designs["gv50_test1"]
+    X, y = tr[:, :9], tr[:, 9]
+    s2 = float(np.var(y, ddof=1))
+
+    def fn(theta):
+        rows = [orc.logpost(X, th, y, s2, orc.FAMILY_ISO, "G") for th in np.atleast_2d(theta)]
+        return dict(val=np.array([r["val"] for r in rows]), beta=np.array([r["beta"] for r in rows]))
+
+    lap = samplers.laplace_batch(fn, np.array([[1.0, 1.0, 0.0]]))
+    ch = samplers.Metro_multichain(lap["mode"], lap["var"][0], 600, 400, 20, 0.5, fn, np.random.default_rng(2))[0]
+    th = ch["sample"][::8]                                                      # 50 thinned posterior rows
+    nat = np.column_stack([1.0 / (1.0 + np.exp(-th[:, 2])), np.exp(th[:, 0]), np.exp(th[:, 1])])
+    mean, _ = orc.predict_table(X, y, s2, orc.FAMILY_ISO, nat, te[:, :9])
+    yhat = mean.mean(axis=1)
+    rm = lambda a, b: float(np.sqrt(np.mean((a - b) ** 2)))                   # noqa: E731
+    assert 2.5 < rm(yhat, stored["y_true"]) < 2.95                              # the reference's run: 2.7219
+    assert rm(yhat, stored["y_hat_combined"]) < 0.35
+    assert np.corrcoef(yhat, stored["y_hat_combined"])[0, 1] > 0.993
