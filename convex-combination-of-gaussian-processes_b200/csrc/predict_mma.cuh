@@ -197,21 +197,27 @@ __global__ void __launch_bounds__(PM_NW * 32, 2) predict_mma_kernel(const Predic
                     if (j1 >= n) v1 = 0.0;
                     cur[g] = make_double2(v0, v1);
                 }
-                // cur[g] -= V'(g, J) L(c, J)' for the panels already solved
-                {
+                // cur[g] -= V'(g, J) L(c, J)' for the panels already solved (operands of panel J+1 are loaded before the
+                // DMMAs of panel J issue; the load past the last panel reads valid shared memory and is discarded)
+                if (c > 0) {
                     const double* bp = Ll + 64 * c;                    // tile (c, 0)
                     int inc = 8 * npad - 64;
-                    for (int J = 0; J < c; ++J) {
-                        const double2 b = ld2(bp);
-                        const double bx = negd(b.x), by = negd(b.y);
-                        double2 a[PM_G];
+                    double2 b = ld2(bp), a[PM_G], an[PM_G];
 #pragma unroll
-                        for (int g = 0; g < PM_G; ++g) a[g] = ld2(vb + (g * NJ + J) * 64 + 2 * lane);
+                    for (int g = 0; g < PM_G; ++g) a[g] = ld2(vb + (g * NJ) * 64 + 2 * lane);
+                    for (int J = 0; J < c; ++J) {
+                        bp += inc; inc -= 64;
+                        const double2 bn = ld2(bp);
+#pragma unroll
+                        for (int g = 0; g < PM_G; ++g) an[g] = ld2(vb + (g * NJ + J + 1) * 64 + 2 * lane);
+                        const double bx = negd(b.x), by = negd(b.y);
 #pragma unroll
                         for (int g = 0; g < PM_G; ++g) mma884(cur[g].x, cur[g].y, a[g].x, bx);
 #pragma unroll
                         for (int g = 0; g < PM_G; ++g) mma884(cur[g].x, cur[g].y, a[g].y, by);
-                        bp += inc; inc -= 64;
+                        b = bn;
+#pragma unroll
+                        for (int g = 0; g < PM_G; ++g) a[g] = an[g];
                     }
                 }
                 const double2 li = ld2(linv_all + 64 * c + 2 * lane);
