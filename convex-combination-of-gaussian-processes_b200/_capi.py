@@ -15,7 +15,7 @@ SYMBOLS = [
     "ccgp_nll_batch", "ccgp_nll_batch_dev", "ccgp_argmin_dev", "ccgp_nll_argmin", "ccgp_rinv_batch",
     "ccgp_predict", "ccgp_predict_dev", "ccgp_me_schur_batch", "ccgp_me_schur_batch_dev", "ccgp_me_argmin",
     "ccgp_subset_logdet_batch", "ccgp_subset_logdet_batch_dev", "ccgp_mixed_corr", "ccgp_debug_phase_timing",
-    "ccgp_kmedoids_pam", "ccgp_me_schur_paired", "ccgp_me_schur_stencil",
+    "ccgp_kmedoids_pam", "ccgp_me_schur_paired", "ccgp_me_schur_stencil", "ccgp_rcond_batch",
 ]
 
 _lib = None
@@ -57,6 +57,7 @@ def load():
     lib.ccgp_argmin_dev.argtypes = [vp, dp, i64, P(f64), P(i64)]
     lib.ccgp_nll_argmin.argtypes = [vp, i32, i32, dp, i64, i64, f64, i32, f64, P(f64), P(i64)]
     lib.ccgp_rinv_batch.argtypes = [vp, i32, i32, dp, i64, i64, dp, dp, ip]
+    lib.ccgp_rcond_batch.argtypes = [vp, i32, i32, dp, i64, i64, dp, dp, ip]
     pred = [vp, i32, dp, i64, i64, i32, dp, i64, dp, i64, f64, dp, dp, ip]
     lib.ccgp_predict.argtypes = pred
     lib.ccgp_predict_dev.argtypes = pred

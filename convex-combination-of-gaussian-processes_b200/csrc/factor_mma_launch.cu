@@ -48,6 +48,8 @@ static int launch_factor_team(ccgp_ctx* ctx, FactorArgs& A, int* launched) {
     A.team_smem_bytes = (int64_t)tsm;
     A.dbg = ctx->dbg;
     A.nparams = (A.family == FAM_ANISO) ? A.d + 2 : 3;
+    A.team_map = env_int("CCGP_TEAM_MAP", 0);
+    if (A.team_map == 2 && var->nw != 4) A.team_map = 0;
     fn<<<(unsigned)grid, threads, smem, ctx->stream>>>(A);
     CK(cudaGetLastError());
     ctx->launches++;

@@ -113,7 +113,15 @@ __global__ void __launch_bounds__(TEAMS_PER_CTA * NW * 32, MINB) factor_team_ker
     extern __shared__ __align__(16) double smem_all[];
     const Layout& lay = A.lay;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int team = wid & (TEAMS_PER_CTA - 1), role = wid / TEAMS_PER_CTA;
+    // warp -> (team, role).  Warp w runs on sub-partition w mod 4 (tools/ubench_smsp.cu):
+    //   map 0: team = w mod 4, role = w / 4   -- a team's warps share ONE sub-partition
+    //   map 1: role = w / 4, team = (w mod 4 - role) mod 4 -- every sub-partition hosts the chain warp of one
+    //          team and update warps of two OTHER teams (their stalls are uncorrelated)
+    //   map 2: team = w / NW, role = w mod NW -- (NW = 4) all chain warps on sub-partition 0, update warps on 1..3
+    int team, role;
+    if (A.team_map == 1) { role = wid / TEAMS_PER_CTA; team = ((wid & 3) - role) & 3; }
+    else if (A.team_map == 2) { team = wid / NW; role = wid - team * NW; }
+    else { team = wid & (TEAMS_PER_CTA - 1); role = wid / TEAMS_PER_CTA; }
     double* etab = smem_all;
     double* Ls = smem_all + 128 + (size_t)team * (A.team_smem_bytes / 8);
     double* Xs = Ls + lay.total;

@@ -185,8 +185,10 @@ __global__ void __launch_bounds__(TEAM, MINB) predict_kernel(const PredictArgs P
 
 struct RinvArgs {
     FactorArgs F;
-    double* out_rinv;  // n*n per candidate, column-major
+    double* out_rinv;  // n*n per candidate, column-major (may be NULL: only beta / rcond wanted)
     double* out_beta;
+    double* out_rcond; // 1 / (||R||_1 ||R^-1||_1), both norms exact: what base R's solve() tests against
+                       // .Machine$double.eps ([A]:448-449; LAPACK dgecon ESTIMATES the same quantity) (may be NULL)
     int32_t* status;
 };
 
@@ -240,7 +242,8 @@ __global__ void __launch_bounds__(TEAM, MINB) rinv_kernel(const RinvArgs P) {
             if (P.status) P.status[s] = bad ? 1 : 0;
         }
         double* v = vbuf + warp * npad;
-        double* out = P.out_rinv + s * (int64_t)n * n;
+        double* out = P.out_rinv ? P.out_rinv + s * (int64_t)n * n : nullptr;
+        double inv1 = 0.0, r1 = 0.0;                 // this warp's largest column 1-norms of R^-1 and of R
         for (int t = warp; t < n; t += TEAM / 32) {
             // forward: v = L^-1 e_t  (zero above t)
             for (int i = lane; i < n; i += 32) v[i] = (i == t) ? 1.0 : 0.0;
@@ -265,8 +268,38 @@ __global__ void __launch_bounds__(TEAM, MINB) rinv_kernel(const RinvArgs P) {
                 if (lane == 0) v[k] = xk;
                 __syncwarp();
             }
-            for (int i = lane; i < n; i += 32) out[i + (int64_t)n * t] = bad ? nanv : v[i];
+            if (out) for (int i = lane; i < n; i += 32) out[i + (int64_t)n * t] = bad ? nanv : v[i];
+            if (P.out_rcond) {
+                double ca = 0.0, cr = 0.0;
+                for (int i = lane; i < n; i += 32) {
+                    ca += fabs(v[i]);
+                    double rv = 1.0;
+                    if (i != t) {
+                        if (prm->kind != 0) {
+                            rv = corr1d(prm, fabs(Xs[i] - Xs[t]));
+                        } else {
+                            double s1 = 0.0;
+                            for (int k = 0; k < d; ++k) { const double df = Xs[k * npx + i] - Xs[k * npx + t]; s1 = fma(prm->wts[k] * df, df, s1); }
+                            rv = fma(prm->b, dexp_neg(prm->rho * s1), prm->a * dexp_neg(s1));
+                        }
+                    }
+                    cr += fabs(rv);
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) { ca += __shfl_xor_sync(0xffffffffu, ca, o); cr += __shfl_xor_sync(0xffffffffu, cr, o); }
+                inv1 = fmax(inv1, ca); r1 = fmax(r1, cr);
+            }
             __syncwarp();
+        }
+        if (P.out_rcond) {
+            __syncthreads();
+            if (lane == 0) { red[2 * warp] = inv1; red[2 * warp + 1] = r1; }
+            __syncthreads();
+            if (tid == 0) {
+                double a1 = 0.0, b1 = 0.0;
+                for (int w = 0; w < TEAM / 32; ++w) { a1 = fmax(a1, red[2 * w]); b1 = fmax(b1, red[2 * w + 1]); }
+                P.out_rcond[s] = bad ? 0.0 : 1.0 / (a1 * b1);
+            }
         }
     }
 }

@@ -151,6 +151,17 @@ class Engine:
         # each n x n block is column-major; R^-1 is symmetric so the transpose view is the same matrix
         return rinv.transpose(0, 2, 1), beta, status
 
+    def rcond_batch(self, cand, family, scale=NATURAL):
+        """-> (rcond[B], beta[B], status[B]): 1 / (||R||_1 ||R^-1||_1), the number base R's solve() tests
+        against .Machine$double.eps ([A]:448-449)."""
+        cand = _f(np.atleast_2d(cand))
+        B, k = cand.shape
+        rc = np.empty(B)
+        beta = np.empty(B)
+        status = np.empty(B, dtype=np.int32)
+        self._ck(self._lib.ccgp_rcond_batch(self._h, family, scale, _ptr(cand), B, B, _ptr(rc), _ptr(beta), _ptr(status)))
+        return rc, beta, status
+
     # -- prediction ---------------------------------------------------------------
     def predict(self, pars, family, X_new, sigma2, pars_vec=None, vec_family=-1):
         """-> (mean[T,S], var[T,S], status[S])."""

@@ -97,15 +97,27 @@ def cross_corr_matrix(D_old, D_new, theta, engine=None):
 
 
 # ---- L2: likelihood -----------------------------------------------------------------
-def logpost_batch(D_train, theta, y, sigma2, script="A", prior_pars=None, engine=None, want_rinv=False):
+R_EPS = 2.220446049250313e-16      # .Machine$double.eps, solve()'s default tol
+
+
+def logpost_batch(D_train, theta, y, sigma2, script="A", prior_pars=None, engine=None, want_rinv=False, na_rule="rcond"):
     """Batched `logpost`: theta is a (B x k) matrix of real-line rows.
-    -> dict(val[B], beta[B], loglik[B], status[B][, R_Inv[B,n,n]]); NaN where R gives NA ([A]:448-449)."""
+    -> dict(val[B], beta[B], loglik[B], status[B][, R_Inv[B,n,n]]); NaN where R gives NA ([A]:448-449).
+    na_rule "rcond" (default) reproduces `try(solve(R))`: NA when the factorisation breaks down (status 1) or
+    rcond_1(R) < .Machine$double.eps (status 2; one extra ccgp_rcond_batch call); "pivot" keeps only status 1."""
     eng = engine or default_engine()
     family = _SCRIPT_FAMILY[script]
     D = np.atleast_2d(D_train)
     eng.set_design(D, y)
     th = np.atleast_2d(np.asarray(theta, dtype=np.float64))
     nll, beta, status = eng.nll_batch(th, family, sigma2, scale=LOGSCALE)
+    if na_rule == "rcond":
+        rc, _, _ = eng.rcond_batch(th, family, scale=LOGSCALE)
+        na = (status == 0) & ~(rc >= R_EPS)
+        status = status.copy()
+        status[na] = 2
+        nll = np.where(na, np.nan, nll)
+        beta = np.where(na, np.nan, beta)
     val = -nll + log_jacobian(th, family, D.shape[1]) + log_prior(th, script, prior_pars)
     out = dict(val=val, beta=beta, loglik=-nll, status=status)
     if want_rinv:

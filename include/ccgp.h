@@ -113,6 +113,13 @@ int ccgp_nll_argmin(ccgp_ctx* ctx, int family, int scale, const double* cand, in
  * out_Rinv is n*n*B (each n x n column-major), out_beta B. */
 int ccgp_rinv_batch(ccgp_ctx* ctx, int family, int scale, const double* cand, int64_t B, int64_t ldc,
                     double* out_Rinv, double* out_beta, int32_t* out_status);
+/* rcond_1(R) = 1 / (||R||_1 ||R^-1||_1) per candidate (both norms exact, from the explicit inverse):
+ * the number base R's solve() compares with .Machine$double.eps before logpost's `try(solve(R))`
+ * turns into NA ([A]:448-449; R takes LAPACK dgecon's ESTIMATE of it).  The R / Python `logpost`
+ * wrappers return NA when status != 0 or rcond < 2.220446e-16.  out_rcond[b] = 0 when the
+ * factorisation itself broke down (status 1).  out_beta / out_status may be NULL. */
+int ccgp_rcond_batch(ccgp_ctx* ctx, int family, int scale, const double* cand, int64_t B, int64_t ldc,
+                     double* out_rcond, double* out_beta, int32_t* out_status);
 
 /* ---- prediction table: predict.post [A]:604-623 over S posterior rows x T sites
  * pars is S x k natural-scale (family); Xnew is T x d column-major.

@@ -69,7 +69,7 @@ def test_nll_iso_gls_golden(engine, golden, designs, case, key, n_s2):
     ok = golden[case + "_kappa"] <= 1e6
     assert np.all(st[ok] == 0)
     assert rel_err(-nll[ok], golden[case + "_ref"][ok]).max() < TOL
-    assert rel_err(beta[ok], golden[case + "_beta"][ok]).max() < 1e-9   # beta carries kappa*eps directly
+    assert rel_err(beta[ok], golden[case + "_beta"][ok]).max() < TOL    # observed max 1.6e-11 at kappa_1 = 4.7e5 (profiles/r02_parity_errors.txt)
     tr = golden[case + "_truth"]
     okt = ~np.isnan(tr)
     assert rel_err(-nll[okt], tr[okt]).max() < TOL
@@ -142,7 +142,7 @@ def test_nll_random_designs_vs_oracle(engine, n, d, family):
         assert kappa < 1e6
         assert st[b] == 0
         assert rel_err(-nll[b], o["loglik"]) < TOL, (n, d, b)
-        assert rel_err(beta[b], o["beta"]) < 1e-9
+        assert rel_err(beta[b], o["beta"]) < TOL
         m = orc.loglik_minimal(X, y, 1.7, of, nat[b], "tau", 25.0)
         assert rel_err(-nll_t[b], m["loglik"]) < TOL
 
@@ -210,8 +210,10 @@ def test_choose_hyperpars_matches_oracle_rows(engine, golden, designs):
     rows = golden["c1n14_likeli_rows"].astype(int)
     for i, want in zip(rows, golden["c1n14_likeli"]):
         got = api.likeli_hyperpars(X, golden["c1n14_y"], hp[i, 0:2], hp[i, 2:4], 0.7, N=N, tau=100.0, engine=engine)
-        # the oracle's value carries the reference's own 1e-8 error in this variant; compare logs
-        assert abs(np.log(got) - np.log(want)) < 1e-6
+        # the oracle's value carries the reference's own error in this variant (2.5e-8 per candidate, c1n14 rows of
+        # profiles/r02_parity_errors.txt; observed difference of the logs 8.5e-10); the gate against the accurate path is
+        # test_nll_tau_variant_vs_truth / test_heat_exchanger_choose_hyperpars_rows (1e-10)
+        assert abs(np.log(got) - np.log(want)) < 1e-8
     res = api.choose_hyperpars(X, golden["c1n14_y"], hp, 0.7, N=1728, tau=100.0, engine=engine)
     assert res["likelihoods"].shape == (60,) and np.all(res["likelihoods"] > 0)
     assert np.array_equal(res["pars"], hp[int(np.argmax(res["likelihoods"]))])
@@ -223,22 +225,22 @@ def test_predict_golden_tables(engine, golden, designs):
     m, v, st = engine.predict(golden["pred14_pars"], GAUSS_ANISO_LAMBDA, golden["pred14_Xnew"], 0.9)
     assert np.all(st == 0)
     assert rel_err(m, golden["pred14_mean"]).max() < TOL
-    assert np.abs(v - golden["pred14_var"]).max() < 1e-9        # var ~ 1 - r'R^-1 r cancels: absolute, kappa*eps
+    assert np.abs(v - golden["pred14_var"]).max() < TOL * 0.9   # var = sigma2 (1 - r'R^-1 r + ..) cancels: absolute, in units of sigma2
     # quirk Q2 ([V]:672)
     m, v = api.predict_post_batch(golden["pred14_Xnew"], designs["maximin14"], golden["pred14_y"], golden["predV_pars"], 0.9,
                                   script="V", engine=engine)
     assert rel_err(m, golden["predV_mean"]).max() < TOL
-    assert np.abs(v - golden["predV_var"]).max() < 1e-9
+    assert np.abs(v - golden["predV_var"]).max() < TOL * 0.9
     he, het = designs["he_train"], designs["he_test"]
     engine.set_design(he[:, :4], he[:, 4])
     m, v, _ = engine.predict(golden["predHE_pars"], GAUSS_ISO, het[:, :4], 30.0)
-    assert rel_err(m, golden["predHE_mean"]).max() < 1e-9
-    assert np.abs(v - golden["predHE_var"]).max() / 30.0 < 1e-8
+    assert rel_err(m, golden["predHE_mean"]).max() < TOL        # observed 2.3e-12 / 2.7e-12 at kappa_1 = 1.35e6
+    assert np.abs(v - golden["predHE_var"]).max() / 30.0 < TOL
     tr, te = designs["gv50_train1"], designs["gv50_test1"]
     engine.set_design(tr[:, :9], tr[:, 9])
     m, v, _ = engine.predict(golden["predGV_pars"], GAUSS_ISO, te[:20, :9], 13.0)
     assert rel_err(m, golden["predGV_mean"]).max() < TOL
-    assert np.abs(v - golden["predGV_var"]).max() / 13.0 < 1e-9
+    assert np.abs(v - golden["predGV_var"]).max() / 13.0 < TOL
     one = api.predict_post(te[0, :9], tr[:, :9], tr[:, 9], golden["predGV_pars"][0], 13.0, script="G", engine=engine)
     assert one.shape == (1, 2) and rel_err(one[0, 0], golden["predGV_mean"][0, 0]) < TOL
 
@@ -279,7 +281,7 @@ def test_me_schur_golden_and_selection(engine, golden, designs):
     D_old, pool = designs["me_initial14"], designs["me_all_subdesigns"]
     nd, ld, st = engine.me_schur_batch(D_old, pool[:200], golden["me_params"])
     assert np.all(st == 0)
-    assert rel_err(nd, golden["me_negdet_200"]).max() < 1e-9
+    assert (np.abs(nd - golden["me_negdet_200"]) / np.abs(golden["me_negdet_200"])).max() < TOL   # each value, 1.9e-15 .. 1.2e-2; observed 4.4e-12
     assert np.abs(nd - golden["me_negdet_200"]).max() / np.abs(golden["me_negdet_200"]).max() < TOL
     assert np.array_equal(nd.argmin(axis=0), golden["me_argmin_200"])          # bit-exact selection
     assert np.allclose(ld, np.log(-nd), rtol=0, atol=1e-12)

@@ -21,7 +21,11 @@ eng.set_design(X, y)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 configs = [("auto", {}), ("team nw4", {"CCGP_KERNEL": "3", "CCGP_TEAM_NW": "4"}), ("team nw3", {"CCGP_KERNEL": "3", "CCGP_TEAM_NW": "3"}), ("team nw3 fused", {"CCGP_KERNEL": "3", "CCGP_TEAM_NW": "3", "CCGP_TEAM_FUSED": "1"}),
            ("team nw2", {"CCGP_KERNEL": "3", "CCGP_TEAM_NW": "2"}), ("warp", {"CCGP_KERNEL": "1"}),
-           ("cta nw4", {"CCGP_KERNEL": "4"}), ("dfma", {"CCGP_NO_MMA": "1"})]
+           ("cta nw4", {"CCGP_KERNEL": "4"}), ("dfma", {"CCGP_NO_MMA": "1"}),
+           ("team nw3 map1", {"CCGP_KERNEL": "3", "CCGP_TEAM_NW": "3", "CCGP_TEAM_MAP": "1"}),
+           ("team nw2 map1", {"CCGP_KERNEL": "3", "CCGP_TEAM_NW": "2", "CCGP_TEAM_MAP": "1"}),
+           ("team nw4 map1", {"CCGP_KERNEL": "3", "CCGP_TEAM_NW": "4", "CCGP_TEAM_MAP": "1"}),
+           ("team nw4 map2", {"CCGP_KERNEL": "3", "CCGP_TEAM_NW": "4", "CCGP_TEAM_MAP": "2"})]
 extra = os.environ.get("TIME_NLL_CONFIGS")
 if extra:
     configs = [c for c in configs if c[0] in extra.split(",")]
@@ -33,7 +37,7 @@ for B in Bs:
     beta = torch.empty(B, dtype=torch.float64, device=dev)
     status = torch.empty(B, dtype=torch.int32, device=dev)
     for name, env in configs:
-        for k in ("CCGP_MMA_NW", "CCGP_NO_MMA", "CCGP_TEAM_NW", "CCGP_TEAM_FUSED", "CCGP_KERNEL"):
+        for k in ("CCGP_MMA_NW", "CCGP_NO_MMA", "CCGP_TEAM_NW", "CCGP_TEAM_FUSED", "CCGP_KERNEL", "CCGP_TEAM_MAP"):
             os.environ.pop(k, None)
         os.environ.update(env)
         ts = []
