@@ -31,6 +31,9 @@ P_PAIRS = N_PTS * (N_PTS - 1) // 2
 FLOP_PER_EVAL = P_PAIRS * (4 * DIM + 3) + (N_PTS ** 3 / 3 + N_PTS ** 2 / 2 + N_PTS / 6) + 2 * N_PTS ** 2 + 6 * N_PTS
 EXP_PER_EVAL = 2 * P_PAIRS
 BYTES_PER_EVAL = 52  # 32 B candidate row in, nll + beta + status out
+# SURVEY 8(d) ME Schur determinant (n_old = 14, n_new = 7, d = 2 iso): 4 860 FLOP + 238 exp; 112 B design in + 12 B out.
+# One table-driven exp is 10 FP64 pipe instructions (ccgp_math.h), i.e. 20 FLOP-equivalents of the same pipe.
+ME_FLOP, ME_EXP, ME_EXP_FLOP_EQ, ME_BYTES = 4860.0, 238.0, 20.0, 124.0
 
 
 def parse():
@@ -43,6 +46,10 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="candidates in the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-me", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --batch candidates per GPU (default). strong: ONE --batch-candidate batch split over the ranks, "
+                         "the which.min all-reduce inside the timed region; the headline value then is the strong-scaling one")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling block of the default run")
     return ap.parse_args()
 
 
@@ -56,6 +63,13 @@ def _cpu_worker(args):
         nat = orc.transform_theta(orc.FAMILY_ANISO_LAMBDA, t, 2)
         out[i] = orc.loglik_reference(X, y, s2, orc.FAMILY_ANISO_LAMBDA, nat)["loglik"]
     return out
+
+
+def _cpu_me_worker(args):
+    os.environ["OPENBLAS_NUM_THREADS"] = "1"
+    from oracle import ccgp_oracle as orc
+    D_old, pool, prm = args
+    return orc.me_schur_negdet_batch(D_old, pool, prm)
 
 
 class CpuArm:
@@ -206,7 +220,10 @@ def run_ours(args, rank, world, local_rank):
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
+    # roofline denominators, measured BEFORE the clock sampler starts (their kernels are not part of the timed region)
     peak = eng.measure_fp64_peak()
+    peak_dmma = eng.measure_fp64_peak_dmma()
+    barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     launches0 = eng.launch_count
     barrier()
@@ -279,9 +296,51 @@ def run_ours(args, rank, world, local_rank):
             t = torch.tensor([me_ms], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             me_ms = float(t.item())
+        me_kern_s = me_ms * 1e-3 / me_steps
+        me_tf = ME_FLOP * 1000 * P / me_kern_s / 1e12
+        me_tf_exp = (ME_FLOP + ME_EXP * ME_EXP_FLOP_EQ) * 1000 * P / me_kern_s / 1e12
+        # e2e: host buffers through ccgp_me_argmin (H2D of the designs + parameter rows, D2H of the P (value, index) pairs)
+        eng.set_stream(None)
+        eng.me_argmin(D_old, pool, params)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(me_steps):
+            bv_me, bi_me = eng.me_argmin(D_old, pool, params)
+        barrier()
+        me_e2e_s = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([me_e2e_s], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            me_e2e_s = float(t.item())
+        eng.set_stream(stream.cuda_stream)
+        me_cpu = None
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            import multiprocessing as mp
+            cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
+            rows = 4 * cores                                    # 1000 designs x rows parameter rows: a few seconds
+            with mp.get_context("fork").Pool(cores) as pl:
+                pl.map(_cpu_me_worker, [(D_old, pool[:8], params[:1])] * cores)
+                t0 = time.perf_counter()
+                parts = pl.map(_cpu_me_worker, [(D_old, pool, params[i:i + 4]) for i in range(0, rows, 4)])
+                dt = time.perf_counter() - t0
+            nd_cpu = np.hstack(parts)
+            same = bool(np.array_equal(nd_cpu.argmin(axis=0), bi_me[:rows]))
+            me_cpu = {"value": 1000 * rows / dt, "unit": "dets/s", "cores": cores, "kind": "port",
+                      "sample": "1000 designs x first %d parameter rows, oracle Augmented.Mixed.Entropy (cross Grams, solve(R.old) once per row, "
+                                "dgetrf det), 1 process/core" % rows, "argmin_identical_to_gpu": same}
         me = {"metric": "ME subset (Schur) log-dets/sec", "value": world * 1000 * P * me_steps / (me_ms * 1e-3),
               "unit": "dets/s", "workload": "ME-A: Initial ME Design (14x2) + 1000 All_Subdesigns blocks x 1000 parameter rows per GPU per step",
-              "ms_per_step": me_ms / me_steps}
+              "ms_per_step": me_ms / me_steps,
+              "roofline": {"bound": "tensor", "bound_detail": "FP64 pipe (DFMA); 7x7 Schur blocks are too small for DMMA tiles",
+                           "achieved": me_tf, "peak": peak / 1e12, "unit": "TFLOP/s", "frac": me_tf / (peak / 1e12),
+                           "achieved_with_exp": me_tf_exp, "frac_with_exp": me_tf_exp / (peak / 1e12),
+                           "flop_per_det": ME_FLOP, "exp_per_det": ME_EXP, "exp_flop_equivalent": ME_EXP_FLOP_EQ,
+                           "hbm": {"achieved_gbs": (112.0 * 1000 + 8.0 * 1000 * P) / me_kern_s / 1e9, "peak_gbs": None},
+                           "traffic": None},
+              "cpu_baseline": me_cpu,
+              "e2e": {"value": world * 1000 * P * me_steps / me_e2e_s, "unit": "dets/s",
+                      "h2d_bytes_per_step": int(1000 * 14 * 8 + P * 24 + 14 * 2 * 8), "d2h_bytes_per_step": int(P * 16),
+                      "timed": "wall clock around %d synchronous ccgp_me_argmin host calls (1000 designs x %d rows each)" % (me_steps, P)}}
         # ---- predictive table (the prediction() stage of the same fit): S posterior rows x T = 625 grid sites, n = 100
         S_p, T_p = 1000, 625
         rng_p = np.random.default_rng(4242 + rank)
@@ -313,6 +372,52 @@ def run_ours(args, rank, world, local_rank):
                 "ms_per_step": p_ms / me_steps, "tflops_algorithmic": pflop * me_steps / (p_ms * 1e-3) / 1e12,
                 "finite": bool(torch.isfinite(pm).all().item())}
         eng.set_stream(None)
+
+    # ---- strong scaling: ONE batch split over the ranks through the host-pointer call (H2D + kernel + D2H of the rank's
+    # slice), then the path's collective -- which.min as two NCCL all-reduces -- INSIDE the timed region.  Three batches:
+    # the headline 2^20 stream and the reference's own sweeps ([V]:552-599: 60 x 1728 at n = 14; [H]:549-595: 624 x 1000 at n = 64).
+    strong = None
+    if not args.no_strong:
+        from ccgp_b200 import reference_api as api
+        from ccgp_b200 import GAUSS_ISO, MEAN_ZERO_PLUS_TAU2
+        eng.set_stream(None)
+        strong = {}
+
+        def timed_split(tag, Xd, yd, cand, family, sigma2, scale, mean_mode, tau, reps):
+            eng.set_design(Xd, yd)
+            total = cand.shape[0]
+            lo, hi = sharding.shard_range(total, rank, world)
+            mine = np.asfortranarray(cand[lo:hi])
+            best = None
+            for it in range(reps + 1):
+                barrier()
+                t0 = time.perf_counter()
+                h_nll, _, _ = eng.nll_batch(mine, family, sigma2, scale=scale, mean_mode=mean_mode, tau=tau)
+                i = int(np.nanargmin(h_nll)) if np.isfinite(h_nll).any() else -1
+                g = sharding.allreduce_argmin(float(h_nll[i]) if i >= 0 else float("nan"), lo + i if i >= 0 else -1, device=dev)
+                torch.cuda.synchronize(dev)
+                dt = time.perf_counter() - t0
+                if world > 1:
+                    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                    dt = float(t.item())
+                if it > 0:
+                    best = dt if best is None else min(best, dt)
+            strong[tag] = {"candidates": int(total), "ms": best * 1e3, "value": total / best, "unit": "evals/s",
+                           "argmin": {"nll": g[0], "index": g[1]}}
+
+        timed_split("m1_2^20_n100", X, y, workloads.m1_candidates(1 << 20, seed=20131), GAUSS_ANISO_LAMBDA, s2, LOGSCALE, 0, 0.0, 3)
+        dsg = workloads.designs()
+        X14 = dsg["maximin14"]
+        hp = dsg["hyperpars_2d"]
+        c14 = np.vstack([api.sweep_candidates(hp[i, 0:2], hp[i, 2:4], 1728) for i in range(hp.shape[0])])
+        timed_split("choose_hyperpars_60x1728_n14", X14, workloads.test_function_4(X14), c14, GAUSS_ISO, 0.7, 0, MEAN_ZERO_PLUS_TAU2, 100.0, 5)
+        he, hph = dsg["he_train"], dsg["he_hyperpars"]
+        c64 = np.vstack([api.sweep_candidates(hph[i, 0:2], hph[i, 2:4], 1000) for i in range(hph.shape[0])])
+        timed_split("choose_hyperpars_624x1000_n64", he[:, :4], he[:, 4], c64, GAUSS_ISO, 30.0, 0, MEAN_ZERO_PLUS_TAU2, 50.0, 5)
+        strong["timed"] = ("per batch: barrier, then wall clock around [ccgp_nll_batch on the rank's contiguous slice (host buffers: H2D, kernel, D2H) + "
+                           "which.min of the slice + 2 NCCL all-reduces (MIN value, MIN index of the winners)], max over ranks, best of the repeats")
+        eng.set_design(X, y)
 
     # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload
     cpu = None
@@ -363,7 +468,11 @@ def run_ours(args, rank, world, local_rank):
                        "argmin": {"nll": gmin[0], "index": gmin[1]}},
             "roofline": {"bound": "tensor", "bound_detail": "FP64 pipe: DFMA and the FP64 tensor form (mma.sync.m8n8k4.f64, DMMA) share it at 64 FMA/clk/SM; tcgen05 has no FP64 kind", "achieved": achieved_tf, "peak": peak / 1e12, "unit": "TFLOP/s",
                          "frac": achieved_tf / (peak / 1e12),
-                         "peak_source": "measured live: dependent-free DFMA loop on all SMs (MEASURED_PEAKS.json has no FP64 entry)",
+                         "peak_source": "measured live before the timed region: dependent-free DFMA loop on all SMs (MEASURED_PEAKS.json has no FP64 entry)",
+                         "peak_detail": {"dfma_loop_tflops": peak / 1e12, "dmma_m8n8k4_loop_tflops": peak_dmma / 1e12,
+                                         "theoretical_tflops": 148 * 128 * 1.965e9 / 1e12,
+                                         "note": "no library DGEMM is linked (libccgp.so has no cuBLAS dependency); the DMMA loop is the GEMM-shaped cross-check"},
+                         "executed_floor": "FP64 pipe time per candidate ~30 k clk of a sub-partition (15 k DMMA + 10.5 k build DFMA + 4.2 k diagonal chain) = 47 % of peak on the FLOP-only count at 100 % pipe occupancy: the 9 900 exponentials are not in flop_per_eval",
                          "flop_per_eval": FLOP_PER_EVAL, "exp_per_eval": EXP_PER_EVAL,
                          "exp_per_s": EXP_PER_EVAL * B / kern_s,
                          "hbm": {"achieved_gbs": BYTES_PER_EVAL * B / kern_s / 1e9, "peak_gbs": hbm_peak,
@@ -374,8 +483,13 @@ def run_ours(args, rank, world, local_rank):
                     "d2h_bytes_per_step": int(B * 20), "timed": "wall clock around %d synchronous ccgp_nll_batch host calls" % ksteps},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "me": me, "predict": pred,
+            "me": me, "predict": pred, "strong": strong,
         }
+        if args.scaling == "strong" and strong:
+            st = strong["m1_2^20_n100"]
+            line.update({"scaling": "strong", "value": st["value"], "ms_per_step": st["ms"],
+                         "weak": {"value": value, "ms_per_step": total_ms / args.steps}})
+            line["config"]["parallelism"] = "ONE batch of 2^20 candidates split contiguously over %d ranks, which.min all-reduce in the timed region" % world
         _emit(line)
     eng.close()
     if world > 1:

@@ -16,6 +16,7 @@ SYMBOLS = [
     "ccgp_predict", "ccgp_predict_dev", "ccgp_me_schur_batch", "ccgp_me_schur_batch_dev", "ccgp_me_argmin",
     "ccgp_subset_logdet_batch", "ccgp_subset_logdet_batch_dev", "ccgp_mixed_corr", "ccgp_debug_phase_timing",
     "ccgp_kmedoids_pam", "ccgp_me_schur_paired", "ccgp_me_schur_stencil", "ccgp_rcond_batch",
+    "ccgp_create_multi", "ccgp_num_gpus", "ccgp_collective_count", "ccgp_measure_fp64_peak_dmma",
 ]
 
 _lib = None
@@ -39,6 +40,10 @@ def load():
     lib.ccgp_num_params.argtypes = [i32, i32]
     lib.ccgp_create.argtypes = [P(vp), i32]
     lib.ccgp_destroy.argtypes = [vp]
+    lib.ccgp_create_multi.argtypes = [P(vp), i32]
+    lib.ccgp_num_gpus.argtypes = [vp]
+    lib.ccgp_collective_count.argtypes = [vp]
+    lib.ccgp_collective_count.restype = i64
     lib.ccgp_last_error.argtypes = [vp]
     lib.ccgp_last_error.restype = C.c_char_p
     lib.ccgp_sync.argtypes = [vp]
@@ -50,6 +55,7 @@ def load():
     lib.ccgp_launch_count.restype = i64
     lib.ccgp_last_nll_config.argtypes = [vp, P(i32), P(i32), P(i32), P(i32)]
     lib.ccgp_measure_fp64_peak.argtypes = [vp, P(f64)]
+    lib.ccgp_measure_fp64_peak_dmma.argtypes = [vp, P(f64)]
     lib.ccgp_set_design.argtypes = [vp, dp, i32, i32, dp]
     nll = [vp, i32, i32, dp, i64, i64, f64, i32, f64, dp, dp, ip]
     lib.ccgp_nll_batch.argtypes = nll
@@ -75,7 +81,7 @@ def load():
     lib.ccgp_kmedoids_pam.argtypes = [vp, dp, i64, i32, i32, i32, ip, dp, ip]
     for s in SYMBOLS:
         fn = getattr(lib, s)
-        if s not in ("ccgp_last_error", "ccgp_launch_count"):
+        if s not in ("ccgp_last_error", "ccgp_launch_count", "ccgp_collective_count"):
             fn.restype = i32
     _lib = lib
     return lib

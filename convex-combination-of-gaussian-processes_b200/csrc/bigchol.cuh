@@ -3,15 +3,17 @@
 //
 // Same likelihood as factor_engine.cuh (logpost [A]:444-455 / cond.like [V]:564-575), same
 // augmented-matrix trick, but every candidate's matrix lives in HBM (column-major, leading
-// dimension nrp) and the factorisation is a right-looking blocked Cholesky, block size 64,
-// one launch per stage and step, batched over the candidates of a chunk:
-//   build    : mixed correlation tiles (2 exp per entry) + identity padding + rows y', 1'
-//   potrf64  : 64x64 diagonal block in shared memory (one CTA per candidate)
-//   trsm64   : rows below, one thread per row against the diagonal block in shared memory
-//   syrk64   : trailing update C_ij -= P_i P_j' on the FP64 tensor path
-//              (mma.sync.m8n8k4.f64 -> DMMA; tcgen05 has no FP64 kind) -- the only place in
-//              this library where the update is a dense contraction big enough to feed it
-//   finish   : z-dots, beta, Q_R, log det -> NLL
+// dimension nrp) and the factorisation is a LEFT-looking blocked Cholesky, block columns of 64,
+// batched over the candidates of a chunk; per block column k:
+//   update<false> : C(rows >= 64k, k) -= sum_{j<k} L(rows, j) L(k, j)'  for all 128-row tiles at once, the whole
+//                   K = 64k contraction accumulated in registers on the FP64 tensor path
+//                   (mma.sync.m8n8k4.f64 -> DMMA; tcgen05 has no FP64 kind), operands staged with cp.async
+//   potrf         : the 64x64 diagonal block in shared memory (one CTA per candidate) + its inverse
+//   update<true>  : rows below = C * inv(L_kk)' on the same tensor path (K = 64) instead of a 64-step substitution
+// plus build (mixed correlation tiles, 2 exp per entry, identity padding, rows y', 1') and finish (z-dots, beta,
+// Q_R, log det -> NLL, or the log-determinant alone for index subsets of a point pool).
+// CCGP_BIG_RIGHT=1 runs the first version of this path (right-looking: potrf, big_trsm_kernel, one K = 64
+// big_syrk_kernel launch per panel) for A/B timing.
 // Row layout: [0,n) design points, [n,ncp) identity padding (ncp = n rounded up to 64),
 // rows ncp and ncp+1 are y' and 1', zero rows up to nrp = ncp + 64.
 #pragma once
@@ -32,12 +34,14 @@ struct BigArgs {
     double* logdet;
     int* bad;
     double* linv;              // per candidate: inv(L_kk)' of the block just factored, linv[q*64 + c] = inv(L_kk)(c, q)
+    const int32_t* idx;        // optional gather (subset log-dets): row i of candidate b is pool row idx[(b0 + b) + ldi * i]
+    int64_t ldi, ldx, b0;      // ldx: leading dimension of X (n for a shared design, pool rows when gathering)
 };
 
 __global__ void __launch_bounds__(128) big_params_kernel(FactorArgs F, int64_t b0, int nb, Prm* prm, double* logdet, int* bad) {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b < nb) {
-        load_params(F, b0 + b, prm + b);
+        load_params(F, F.shared_row ? 0 : b0 + b, prm + b);
         logdet[b] = 0.0;
         bad[b] = 0;
     }
@@ -53,8 +57,13 @@ __global__ void __launch_bounds__(256) big_build_kernel(BigArgs G) {
     for (int e = tid; e < d * 64; e += 256) {
         int k = e / 64, r = e % 64;
         int i = ti * 64 + r, j = tj * 64 + r;
-        xi[k][r] = (i < n) ? G.X[(size_t)k * n + i] : 0.0;
-        xj[k][r] = (j < n) ? G.X[(size_t)k * n + j] : 0.0;
+        if (G.idx) {
+            xi[k][r] = (i < n) ? G.X[(size_t)k * G.ldx + G.idx[(G.b0 + b) + G.ldi * i]] : 0.0;
+            xj[k][r] = (j < n) ? G.X[(size_t)k * G.ldx + G.idx[(G.b0 + b) + G.ldi * j]] : 0.0;
+        } else {
+            xi[k][r] = (i < n) ? G.X[(size_t)k * G.ldx + i] : 0.0;
+            xj[k][r] = (j < n) ? G.X[(size_t)k * G.ldx + j] : 0.0;
+        }
     }
     if (tid < d) wts[tid] = pr->wts[tid];
     __syncthreads();
@@ -72,7 +81,7 @@ __global__ void __launch_bounds__(256) big_build_kernel(BigArgs G) {
                 v = fma(bb, dexp_neg_dev<true>(rho * s1), a * dexp_neg_dev<true>(s1));
             }
         } else if (i == j) v = 1.0;                       // identity padding (i, j in [n, ncp))
-        else if (j < n && i == G.ncp) v = G.y[j];         // row y'
+        else if (j < n && i == G.ncp) v = G.y ? G.y[j] : 0.0;   // row y' (absent in determinant mode)
         else if (j < n && i == G.ncp + 1) v = 1.0;        // row 1'
         Ab[(size_t)j * G.nrp + i] = v;
     }
@@ -370,10 +379,22 @@ __global__ void __launch_bounds__(256) big_finish_kernel(BigArgs G, int64_t b0, 
     }
 }
 
+// determinant mode: log det of every candidate's matrix (the sum of log pivots big_potrf_kernel accumulated)
+__global__ void __launch_bounds__(128) big_logdet_out_kernel(BigArgs G, int nb, double* out_logdet, int32_t* out_status) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    const bool bad = G.bad[b] || !(G.logdet[b] == G.logdet[b]);
+    out_logdet[G.b0 + b] = bad ? __longlong_as_double(0x7ff8000000000000LL) : G.logdet[b];
+    if (out_status) out_status[G.b0 + b] = bad ? 1 : 0;
+}
+
+// d_idx != NULL: determinant mode over index subsets (d_X is then the pool with leading dimension ldx, d_cand ONE
+// shared natural-scale parameter row, d_nll receives log det R[S,S]); otherwise the likelihood of the shared design.
 inline int bigchol_nll_batch(BigCholWorkspace& ws, cudaStream_t stream, int num_sm, const double* d_X, const double* d_y,
                              int n, int d, int family, int scale, const double* d_cand, int64_t B, int64_t ldc,
                              double sigma2, int mean_mode, double tau, double* d_nll, double* d_beta, int32_t* d_status,
-                             int64_t* launches, char* err, size_t errlen) {
+                             int64_t* launches, char* err, size_t errlen,
+                             const int32_t* d_idx = nullptr, int64_t ldi = 0, int64_t ldx = 0) {
 #define BIGCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
         snprintf(err, errlen, "bigchol %s: %s", #call, cudaGetErrorString(e_)); return -2; } } while (0)
     const int ncp = (n + 63) / 64 * 64, nrp = ncp + 64, T = ncp / 64;
@@ -381,7 +402,7 @@ inline int bigchol_nll_batch(BigCholWorkspace& ws, cudaStream_t stream, int num_
     size_t freeb = 0, totalb = 0;
     BIGCK(cudaMemGetInfo(&freeb, &totalb));
     size_t budget = std::min<size_t>((freeb + ws.bytesA) / 2, (size_t)24 << 30);
-    int chunk = (int)std::min<int64_t>(B, std::max<size_t>(1, budget / per));
+    int chunk = (int)std::min<int64_t>(std::min<int64_t>(B, 65535), std::max<size_t>(1, budget / per));   // (grid.z / grid.y limit)
     if (chunk < 1 || per > budget) { snprintf(err, errlen, "n=%d does not fit in device memory", n); return -3; }
     if ((size_t)chunk * per > ws.bytesA || chunk > ws.cap) {
         ws.release();
@@ -401,11 +422,14 @@ inline int bigchol_nll_batch(BigCholWorkspace& ws, cudaStream_t stream, int num_
     memset(&F, 0, sizeof(F));
     F.d = d; F.cand = d_cand; F.ldc = ldc; F.n_params = B; F.family = family; F.logscale = scale; F.sigma2 = sigma2;
     F.force_clamp = 1;
+    F.shared_row = d_idx ? 1 : 0;
     BigArgs G;
     G.A = ws.A; G.n = n; G.d = d; G.ncp = ncp; G.nrp = nrp; G.stride = (int64_t)nrp * ncp;
     G.X = d_X; G.y = d_y; G.prm = ws.prm; G.logdet = ws.logdet; G.bad = ws.bad; G.linv = ws.linv;
+    G.idx = d_idx; G.ldi = ldi; G.ldx = d_idx ? ldx : n; G.b0 = 0;
     for (int64_t b0 = 0; b0 < B; b0 += chunk) {
         const int nb = (int)std::min<int64_t>(chunk, B - b0);
+        G.b0 = b0;
         big_params_kernel<<<(nb + 127) / 128, 128, 0, stream>>>(F, b0, nb, ws.prm, ws.logdet, ws.bad);
         big_build_kernel<<<dim3(T, T + 1, nb), 256, 0, stream>>>(G);
         *launches += 2;
@@ -429,7 +453,8 @@ inline int bigchol_nll_batch(BigCholWorkspace& ws, cudaStream_t stream, int num_
                 *launches += 1;
             }
         }
-        big_finish_kernel<<<nb, 256, 0, stream>>>(G, b0, sigma2, mean_mode, tau, d_nll, d_beta, d_status);
+        if (d_idx) big_logdet_out_kernel<<<(nb + 127) / 128, 128, 0, stream>>>(G, nb, d_nll, d_status);
+        else big_finish_kernel<<<nb, 256, 0, stream>>>(G, b0, sigma2, mean_mode, tau, d_nll, d_beta, d_status);
         *launches += 1;
         BIGCK(cudaGetLastError());
     }

@@ -19,6 +19,7 @@
 using namespace ccgp;
 
 static char g_create_err[512] = "";
+void ccgp_set_create_error(const char* msg) { snprintf(g_create_err, sizeof(g_create_err), "%s", msg); }
 
 // tile table of the trailing-matrix updates: [NJ+1] first-tile index per block column, then one
 // packed entry per TR x TC tile, ordered by block column.  Within a column group (TC columns
@@ -122,8 +123,10 @@ extern "C" int ccgp_create(ccgp_ctx** out, int device) {
 
 extern "C" int ccgp_destroy(ccgp_ctx* ctx) {
     if (!ctx) return CCGP_OK;
+    if (ctx->multi) multi_destroy(ctx);
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->dbg) cudaFree(ctx->dbg);
     for (auto& kv : ctx->tiletabs) cudaFree(kv.second);
     if (ctx->d_X) cudaFree(ctx->d_X);
     if (ctx->d_y) cudaFree(ctx->d_y);
@@ -142,7 +145,7 @@ extern "C" int ccgp_destroy(ccgp_ctx* ctx) {
 
 extern "C" const char* ccgp_last_error(const ccgp_ctx* ctx) { return ctx ? ctx->err : g_create_err; }
 extern "C" int ccgp_device(const ccgp_ctx* ctx) { return ctx ? ctx->device : -1; }
-extern "C" int64_t ccgp_launch_count(const ccgp_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int64_t ccgp_launch_count(const ccgp_ctx* ctx) { return !ctx ? 0 : ctx->launches + (ctx->multi ? multi_launches(ctx) : 0); }
 
 extern "C" int ccgp_set_stream(ccgp_ctx* ctx, void* stream) {
     if (!ctx) return CCGP_ERR_ARG;
@@ -164,6 +167,7 @@ extern "C" int ccgp_set_matern_nu(ccgp_ctx* ctx, double nu) {
     if (!ctx) return CCGP_ERR_ARG;
     const double t2 = 2.0 * nu;
     ARG(nu > 0 && nu <= 50 && t2 == (double)(int)t2);   // integer or half-integer smoothness
+    if (ctx->multi) RC(multi_set_matern_nu(ctx, nu));
     ctx->twonu = (int)t2;
     ctx->mnorm = 1.0 / (tgamma(nu) * pow(2.0, nu - 1.0));
     return CCGP_OK;
@@ -222,12 +226,56 @@ extern "C" int ccgp_measure_fp64_peak(ccgp_ctx* ctx, double* flops) {
     return CCGP_OK;
 }
 
+// ---- FP64 tensor peak: the same pipe driven by mma.sync.m8n8k4.f64 (DMMA), 4 independent accumulators per warp,
+// 8 warps per CTA, 2 CTAs per SM -- the GEMM-shaped cross-check of the DFMA number (no library GEMM is linked)
+__global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters, double seed) {
+    double c[4][2];
+    for (int i = 0; i < 4; ++i) { c[i][0] = seed + i; c[i][1] = seed - i; }
+    const double a = 1.0 + 1e-9 * threadIdx.x, b = 1.0 - 1e-9 * threadIdx.x;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a), "d"(b));
+    }
+    double s = 0;
+    for (int i = 0; i < 4; ++i) s += c[i][0] + c[i][1];
+    if (s == 123.456) out[0] = s;
+}
+
+extern "C" int ccgp_measure_fp64_peak_dmma(ccgp_ctx* ctx, double* flops) {
+    if (!ctx || !flops) return CCGP_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    RC(ensure_ws2(ctx, 64));
+    const int iters = 1 << 14, blocks = ctx->num_sm * 2, threads = 256;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    double best = 0;
+    for (int rep = 0; rep < 4; ++rep) {
+        CK(cudaEventRecord(e0, ctx->stream));
+        dmma_peak_kernel<<<blocks, threads, 0, ctx->stream>>>((double*)ctx->ws2, iters, 1.0);
+        CK(cudaEventRecord(e1, ctx->stream));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        // one warp-wide m8n8k4 = 8*8*4 FMAs = 512 FLOP
+        double f = 512.0 * 4.0 * iters * (double)blocks * (threads / 32) / (ms * 1e-3);
+        if (rep > 0 && f > best) best = f;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *flops = best;
+    return CCGP_OK;
+}
+
 // ------------------------------------------------------------------ design
 extern "C" int ccgp_set_design(ccgp_ctx* ctx, const double* X, int n, int d, const double* y) {
     if (!ctx) return CCGP_ERR_ARG;
     ARG(X != nullptr && y != nullptr);
     ARG(n >= 1 && n <= 32768);
     ARG(d >= 1 && d <= MAXD);
+    if (ctx->multi) RC(multi_set_design(ctx, X, n, d, y));
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
     if (ctx->d_X) { CK(cudaFree(ctx->d_X)); ctx->d_X = nullptr; }
@@ -329,6 +377,7 @@ extern "C" int ccgp_nll_batch(ccgp_ctx* ctx, int family, int scale, const double
     if (rc) return rc;
     ARG(B == 0 || out_nll != nullptr);
     if (B == 0) return CCGP_OK;
+    if (ctx->multi) return multi_nll_batch(ctx, family, scale, cand, B, ldc, sigma2, mean_mode, tau, out_nll, out_beta, out_status);
     CK(cudaSetDevice(ctx->device));
     const int k = ccgp_num_params(family, ctx->d);
     // workspace: cand (B*k) | nll (B) | beta (B) | status (B int32)
@@ -352,29 +401,35 @@ extern "C" int ccgp_nll_batch(ccgp_ctx* ctx, int family, int scale, const double
         return 0;
     };
     // the copy stream must not overtake work already queued on the compute stream that still reads the workspace
-    CK(cudaEventRecord(ctx->ev_kern[0], ctx->stream));
-    CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_kern[0], 0));
-    int64_t prev_b0 = -1, prev_nb = 0;
-    int slot = 0;
-    for (int64_t b0 = 0; b0 < B; b0 += step, slot ^= 1) {
-        const int64_t nb = std::min(step, B - b0);
-        CK(cudaMemcpy2DAsync(d_cand + b0, (size_t)B * 8, cand + b0, (size_t)ldc * 8, (size_t)nb * 8, k, cudaMemcpyHostToDevice,
-                             ctx->copy_stream));
-        CK(cudaEventRecord(ctx->ev_h2d[slot], ctx->copy_stream));
-        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[slot], 0));
-        rc = ccgp_nll_batch_dev(ctx, family, scale, d_cand + b0, nb, B, sigma2, mean_mode, tau, d_nll + b0, d_beta + b0, d_status + b0);
-        if (rc) return rc;
-        CK(cudaEventRecord(ctx->ev_kern[slot], ctx->stream));
-        if (prev_b0 >= 0) {
-            CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_kern[slot ^ 1], 0));
-            if ((rc = fetch(prev_b0, prev_nb))) return rc;
+    auto pipeline = [&]() -> int {
+        CK(cudaEventRecord(ctx->ev_kern[0], ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_kern[0], 0));
+        int64_t prev_b0 = -1, prev_nb = 0;
+        int slot = 0;
+        for (int64_t b0 = 0; b0 < B; b0 += step, slot ^= 1) {
+            const int64_t nb = std::min(step, B - b0);
+            CK(cudaMemcpy2DAsync(d_cand + b0, (size_t)B * 8, cand + b0, (size_t)ldc * 8, (size_t)nb * 8, k, cudaMemcpyHostToDevice,
+                                 ctx->copy_stream));
+            CK(cudaEventRecord(ctx->ev_h2d[slot], ctx->copy_stream));
+            CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[slot], 0));
+            RC(ccgp_nll_batch_dev(ctx, family, scale, d_cand + b0, nb, B, sigma2, mean_mode, tau, d_nll + b0, d_beta + b0, d_status + b0));
+            CK(cudaEventRecord(ctx->ev_kern[slot], ctx->stream));
+            if (prev_b0 >= 0) {
+                CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_kern[slot ^ 1], 0));
+                RC(fetch(prev_b0, prev_nb));
+            }
+            prev_b0 = b0; prev_nb = nb;
         }
-        prev_b0 = b0; prev_nb = nb;
-    }
-    CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_kern[slot ^ 1], 0));
-    if ((rc = fetch(prev_b0, prev_nb))) return rc;
-    CK(cudaStreamSynchronize(ctx->copy_stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_kern[slot ^ 1], 0));
+        RC(fetch(prev_b0, prev_nb));
+        return 0;
+    };
+    rc = pipeline();
+    // every exit -- also a failed one -- waits for the copies still in flight into the caller's buffers
+    cudaError_t e1 = cudaStreamSynchronize(ctx->copy_stream), e2 = cudaStreamSynchronize(ctx->stream);
+    if (rc) return rc;
+    CK(e1);
+    CK(e2);
     return CCGP_OK;
 }
 
@@ -452,6 +507,7 @@ static int argmin_columns(ccgp_ctx* ctx, const double* d_vals, int64_t C, int64_
     argmin_final_kernel<<<(unsigned)P, 256, 0, ctx->stream>>>(part, nparts, d_bv, d_bi);
     CK(cudaGetLastError());
     ctx->launches++;
+    ctx->last_bv_dev = d_bv; ctx->last_bi_dev = d_bi;
     std::vector<long long> hi((size_t)P);
     CK(cudaMemcpyAsync(best_val, d_bv, (size_t)P * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(hi.data(), d_bi, (size_t)P * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -473,6 +529,7 @@ extern "C" int ccgp_nll_argmin(ccgp_ctx* ctx, int family, int scale, const doubl
     int rc = check_nll_args(ctx, family, scale, cand, B, ldc, sigma2, mean_mode);
     if (rc) return rc;
     ARG(B >= 1 && best_nll != nullptr && best_idx != nullptr);
+    if (ctx->multi) return multi_nll_argmin(ctx, family, scale, cand, B, ldc, sigma2, mean_mode, tau, best_nll, best_idx);
     CK(cudaSetDevice(ctx->device));
     const int k = ccgp_num_params(family, ctx->d);
     size_t need = (size_t)B * (k + 1) * 8;
@@ -637,6 +694,8 @@ extern "C" int ccgp_predict(ccgp_ctx* ctx, int family, const double* pars, int64
     if (S == 0 || T == 0) return CCGP_OK;
     ARG(pars && Xnew && out_mean && out_var);
     ARG(family >= 0 && family <= 4);
+    if (ctx->multi && S >= ccgp_num_gpus(ctx))
+        return multi_predict(ctx, family, pars, S, ldp, vec_family, pars_vec, ldpv, Xnew, T, sigma2, out_mean, out_var, out_status);
     CK(cudaSetDevice(ctx->device));
     const int d = ctx->d, k = ccgp_num_params(family, d);
     const int kv = pars_vec ? ccgp_num_params(vec_family, d) : 0;
@@ -663,25 +722,30 @@ extern "C" int ccgp_predict(ccgp_ctx* ctx, int family, const double* pars, int64
         CK(cudaMemcpyAsync(out_var + (size_t)T * s0, d_var + (size_t)T * s0, (size_t)T * ns * 8, cudaMemcpyDeviceToHost, ctx->copy_stream));
         return 0;
     };
-    int slot = 0;
-    int64_t prev_s0 = -1, prev_ns = 0;
-    for (int64_t s0 = 0; s0 < S; s0 += step, slot ^= 1) {
-        const int64_t ns = std::min(step, S - s0);
-        rc = ccgp_predict_dev(ctx, family, d_pars + s0, ns, S, vec_family, pars_vec ? d_pv + s0 : nullptr, S, d_xn, T, sigma2,
-                              d_mean + (size_t)T * s0, d_var + (size_t)T * s0, d_status + s0);
-        if (rc) return rc;
-        CK(cudaEventRecord(ctx->ev_kern[slot], ctx->stream));
-        if (prev_s0 >= 0) {                                  // the previous chunk's table travels while this chunk is computed
-            CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_kern[slot ^ 1], 0));
-            if ((rc = fetch(prev_s0, prev_ns))) return rc;
+    auto pipeline = [&]() -> int {
+        int slot = 0;
+        int64_t prev_s0 = -1, prev_ns = 0;
+        for (int64_t s0 = 0; s0 < S; s0 += step, slot ^= 1) {
+            const int64_t ns = std::min(step, S - s0);
+            RC(ccgp_predict_dev(ctx, family, d_pars + s0, ns, S, vec_family, pars_vec ? d_pv + s0 : nullptr, S, d_xn, T, sigma2,
+                                d_mean + (size_t)T * s0, d_var + (size_t)T * s0, d_status + s0));
+            CK(cudaEventRecord(ctx->ev_kern[slot], ctx->stream));
+            if (prev_s0 >= 0) {                                  // the previous chunk's table travels while this chunk is computed
+                CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_kern[slot ^ 1], 0));
+                RC(fetch(prev_s0, prev_ns));
+            }
+            prev_s0 = s0; prev_ns = ns;
         }
-        prev_s0 = s0; prev_ns = ns;
-    }
-    CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_kern[slot ^ 1], 0));
-    if ((rc = fetch(prev_s0, prev_ns))) return rc;
-    if (out_status) CK(cudaMemcpyAsync(out_status, d_status, (size_t)S * 4, cudaMemcpyDeviceToHost, ctx->copy_stream));
-    CK(cudaStreamSynchronize(ctx->copy_stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_kern[slot ^ 1], 0));
+        RC(fetch(prev_s0, prev_ns));
+        if (out_status) CK(cudaMemcpyAsync(out_status, d_status, (size_t)S * 4, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        return 0;
+    };
+    rc = pipeline();
+    cudaError_t e1 = cudaStreamSynchronize(ctx->copy_stream), e2 = cudaStreamSynchronize(ctx->stream);
+    if (rc) return rc;
+    CK(e1);
+    CK(e2);
     return CCGP_OK;
 }
 
@@ -725,6 +789,7 @@ extern "C" int ccgp_me_schur_batch(ccgp_ctx* ctx, const double* D_old, int n_old
     if (C == 0 || P == 0) return CCGP_OK;
     ARG(D_new && params && (out_negdet || out_logdet));
     ARG(n_old == 0 || D_old != nullptr);
+    if (ctx->multi) return multi_me_schur_batch(ctx, D_old, n_old, d, D_new, n_new, C, params, P, ldq, out_negdet, out_logdet, out_status);
     CK(cudaSetDevice(ctx->device));
     size_t nold_d = (size_t)n_old * d, nnew = (size_t)C * n_new * d, npar = (size_t)P * 3, nout = (size_t)C * P;
     size_t need = (nold_d + nnew + npar + 2 * nout) * 8 + nout * 4;
@@ -833,6 +898,7 @@ extern "C" int ccgp_me_argmin(ccgp_ctx* ctx, const double* D_old, int n_old, int
     ARG(n_old >= 0 && n_new >= 1 && d >= 1 && d <= MAXD && C >= 1 && P >= 1 && ldq >= P);
     ARG(D_new && params && best_val && best_idx);
     ARG(n_old == 0 || D_old != nullptr);
+    if (ctx->multi) return multi_me_argmin(ctx, D_old, n_old, d, D_new, n_new, C, params, P, ldq, best_val, best_idx);
     CK(cudaSetDevice(ctx->device));
     size_t nold_d = (size_t)n_old * d, nnew = (size_t)C * n_new * d, npar = (size_t)P * 3, nout = (size_t)C * P;
     size_t need = (nold_d + nnew + npar + nout) * 8;
@@ -863,7 +929,15 @@ extern "C" int ccgp_subset_logdet_batch_dev(ccgp_ctx* ctx, const double* d_pool,
     const int k = ccgp_num_params(family, d);
     int rc = ensure_ws2(ctx, 64 * 8);
     if (rc) return rc;
-    // params live at the END of ws2's first 64 doubles so argmin scratch (front) never collides mid-stream
+    if (smem_bytes(make_layout(m, 0), d) > (size_t)ctx->max_smem_optin || env_int("CCGP_FORCE_BIG", 0)) {
+        // subsets too large for shared memory (m > ~220; SURVEY 8d ME-B lists m = 256): one HBM matrix per subset,
+        // gathered from the pool, on the blocked tensor path of bigchol.cuh
+        double* d_parb = (double*)ctx->ws2;
+        CK(cudaMemcpyAsync(d_parb, params_host, (size_t)k * 8, cudaMemcpyHostToDevice, ctx->stream));
+        return bigchol_nll_batch(ctx->big, ctx->stream, ctx->num_sm, d_pool, nullptr, m, d, family, 0, d_parb, C, 1, 1.0, 0, 0.0,
+                                 d_logdet, nullptr, d_status, &ctx->launches, ctx->err, sizeof(ctx->err), d_idx, ldi, N);
+    }
+    // the parameter row sits at the FRONT of ws2 (stream order keeps it apart from the argmin scratch that also lives there)
     double* d_par = (double*)ctx->ws2;
     CK(cudaMemcpyAsync(d_par, params_host, (size_t)k * 8, cudaMemcpyHostToDevice, ctx->stream));
     FactorArgs A;

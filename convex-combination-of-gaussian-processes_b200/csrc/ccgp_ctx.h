@@ -39,6 +39,9 @@ struct ccgp_ctx {
     BigCholWorkspace big;
     long long* dbg = nullptr;  // phase-timing buffer (debug)
     int* sm_slots = nullptr;   // per-SM CTA arrival counters of the DMMA kernel
+    double* last_bv_dev = nullptr;     // device results of the last argmin_columns call (value, index per column):
+    long long* last_bi_dev = nullptr;  // what the multi-GPU front end feeds to the NCCL (min, index) all-reduce
+    struct MultiCtx* multi = nullptr;  // multi.cu: set on the front context of ccgp_create_multi
 };
 
 
@@ -77,3 +80,20 @@ int get_tiletab(ccgp_ctx* ctx, const Layout& l, int TR, int TC, const uint32_t**
 // factor_launch.cu / factor_mma_launch.cu
 int launch_factor(ccgp_ctx* ctx, FactorArgs& A);
 int launch_factor_mma(ccgp_ctx* ctx, FactorArgs& A, int* launched);
+// multi.cu -- the front context fans every batch out over its per-GPU contexts
+void ccgp_set_create_error(const char* msg);
+void multi_destroy(ccgp_ctx* front);
+int64_t multi_launches(const ccgp_ctx* front);
+int multi_set_design(ccgp_ctx* front, const double* X, int n, int d, const double* y);
+int multi_set_matern_nu(ccgp_ctx* front, double nu);
+int multi_nll_batch(ccgp_ctx* front, int family, int scale, const double* cand, int64_t B, int64_t ldc, double sigma2,
+                    int mean_mode, double tau, double* out_nll, double* out_beta, int32_t* out_status);
+int multi_nll_argmin(ccgp_ctx* front, int family, int scale, const double* cand, int64_t B, int64_t ldc, double sigma2,
+                     int mean_mode, double tau, double* best_nll, int64_t* best_idx);
+int multi_predict(ccgp_ctx* front, int family, const double* pars, int64_t S, int64_t ldp, int vec_family,
+                  const double* pars_vec, int64_t ldpv, const double* Xnew, int64_t T, double sigma2, double* out_mean,
+                  double* out_var, int32_t* out_status);
+int multi_me_schur_batch(ccgp_ctx* front, const double* D_old, int n_old, int d, const double* D_new, int n_new, int64_t C,
+                         const double* params, int64_t P, int64_t ldq, double* out_negdet, double* out_logdet, int32_t* out_status);
+int multi_me_argmin(ccgp_ctx* front, const double* D_old, int n_old, int d, const double* D_new, int n_new, int64_t C,
+                    const double* params, int64_t P, int64_t ldq, double* best_val, int64_t* best_idx);

@@ -164,6 +164,7 @@ struct FactorArgs {
     long long* dbg;       // optional phase-timing buffer (tools/phase_timing.py); NULL in production
     int* sm_slots;        // DMMA kernel: per-SM arrival counters (zeroed before the launch) -> CTA slot on its SM
     int nparams;          // parameters per candidate row (ccgp_num_params)
+    int shared_row;       // large-n path: 1 = every candidate uses parameter row 0 (subset log-dets)
     int team_map;         // team kernel: warp -> (team, role) mapping, see factor_team.cuh (CCGP_TEAM_MAP)
     double* out0;         // NLL: nll          DET: log det (all pivots)
     double* out1;         // NLL: beta         DET: log det (tail pivots)

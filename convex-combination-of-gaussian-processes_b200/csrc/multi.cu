@@ -73,7 +73,6 @@ extern "C" int ccgp_create_multi(ccgp_ctx** out, int n_gpus) {
     ccgp_ctx* front = nullptr;
     int rc = ccgp_create(&front, 0);
     if (rc) return rc;
-    ccgp_ctx* ctx = front;
     if (n_gpus > count) {
         snprintf(front->err, sizeof(front->err), "ccgp_create_multi: %d GPUs requested, %d visible", n_gpus, count);
         ccgp_set_create_error(front->err);
@@ -103,7 +102,6 @@ extern "C" int ccgp_create_multi(ccgp_ctx** out, int n_gpus) {
             return fail(CCGP_ERR_CUDA);
         }
     }
-    (void)ctx;
     *out = front;
     return CCGP_OK;
 }
@@ -145,7 +143,7 @@ static int fan_out(ccgp_ctx* front, F fn) {
         for (auto& t : th) t.join();
     }
     for (int g = 0; g < M->G; ++g)
-        if (rc[g]) { snprintf(front->err, sizeof(front->err), "GPU %d: %s", g, M->child[g]->err); return rc[g]; }
+        if (rc[g]) { snprintf(front->err, sizeof(front->err), "GPU %d: %.480s", g, M->child[g]->err); return rc[g]; }
     return 0;
 }
 static inline void slice(int64_t total, int g, int G, int64_t* b0, int64_t* nb) {

@@ -27,15 +27,22 @@ def _ptr(a):
 
 
 class Engine:
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, n_gpus: int = None):
+        """device: one GPU (ccgp_create).  n_gpus: all (<= 0) or the first n GPUs of the box behind one context
+        (ccgp_create_multi): batches are sliced over the GPUs inside the library, which.min goes through NCCL."""
         self._lib = _capi.load()
         h = C.c_void_p()
-        rc = self._lib.ccgp_create(C.byref(h), int(device))
+        if n_gpus is None:
+            rc = self._lib.ccgp_create(C.byref(h), int(device))
+            what = "ccgp_create(device=%d)" % device
+        else:
+            rc = self._lib.ccgp_create_multi(C.byref(h), int(n_gpus))
+            what = "ccgp_create_multi(n_gpus=%d)" % n_gpus
         if rc != 0:
-            raise CcgpError("ccgp_create(device=%d) failed (%d): %s" % (
-                device, rc, self._lib.ccgp_last_error(None).decode()))
+            raise CcgpError("%s failed (%d): %s" % (what, rc, self._lib.ccgp_last_error(None).decode()))
         self._h = h
         self.device = device
+        self.n_gpus = self._lib.ccgp_num_gpus(h)
         self.n = 0
         self.d = 0
 
@@ -54,6 +61,10 @@ class Engine:
             self.close()
         except Exception:
             pass
+
+    @property
+    def collective_count(self) -> int:
+        return int(self._lib.ccgp_collective_count(self._h))
 
     def sync(self):
         self._ck(self._lib.ccgp_sync(self._h))
@@ -78,6 +89,11 @@ class Engine:
     def measure_fp64_peak(self) -> float:
         f = C.c_double()
         self._ck(self._lib.ccgp_measure_fp64_peak(self._h, C.byref(f)))
+        return f.value
+
+    def measure_fp64_peak_dmma(self) -> float:
+        f = C.c_double()
+        self._ck(self._lib.ccgp_measure_fp64_peak_dmma(self._h, C.byref(f)))
         return f.value
 
     def set_matern_nu(self, nu: float):

@@ -68,6 +68,19 @@ int ccgp_num_params(int family, int d);
 /* ---- context ------------------------------------------------------------ */
 int ccgp_create(ccgp_ctx** ctx, int device);
 int ccgp_destroy(ccgp_ctx* ctx);
+/* All GPUs of the box behind one context, for a single-threaded caller such as R's .Call:
+ * n_gpus <= 0 takes every visible device.  ccgp_set_design broadcasts the design; ccgp_nll_batch,
+ * ccgp_nll_argmin, ccgp_predict, ccgp_me_schur_batch and ccgp_me_argmin split their batch into contiguous
+ * slices (candidates / posterior rows / parameter rows or designs), one GPU and one host thread per slice,
+ * each GPU writing its slice of the caller's output; per-candidate results are bit-identical for every GPU
+ * count.  which.min ([V]:598, [M]:944-945) is reduced with two NCCL all-reduces (MIN over the values, then MIN
+ * over the indices of the winners: lowest index on ties) on communicators from ncclCommInitAll; libnccl.so.2
+ * is dlopen()ed here (override the path with CCGP_NCCL_LIB), single-GPU contexts never touch it.  Every other
+ * entry point runs on GPU 0 of the set.  The `_dev` variants are single-GPU only. */
+int ccgp_create_multi(ccgp_ctx** ctx, int n_gpus);
+int ccgp_num_gpus(const ccgp_ctx* ctx);
+/* NCCL collectives issued so far by a multi-GPU context (0 for a single-GPU one) */
+int64_t ccgp_collective_count(const ccgp_ctx* ctx);
 const char* ccgp_last_error(const ccgp_ctx* ctx); /* ctx may be NULL: last create error */
 int ccgp_sync(ccgp_ctx* ctx);
 /* Matern smoothness nu of the 1-D families (integer or half-integer, 0 < nu <= 50; default 5) */
@@ -86,6 +99,9 @@ int ccgp_last_nll_config(const ccgp_ctx* ctx, int* team, int* smem_bytes, int* c
 /* measured FP64 FMA throughput of this GPU, FLOP/s, from a dependent-free DFMA
  * loop on every SM (the roofline denominator bench.py reports against) */
 int ccgp_measure_fp64_peak(ccgp_ctx* ctx, double* flops_per_s);
+/* the same pipe driven in its tensor form (mma.sync.m8n8k4.f64 with independent accumulators): the
+ * GEMM-shaped cross-check of the DFMA number; bench.py reports both in roofline.peak_detail */
+int ccgp_measure_fp64_peak_dmma(ccgp_ctx* ctx, double* flops_per_s);
 
 /* ---- training design (D.train, y) shared by every candidate -------------- */
 /* X is n x d column-major, y has n entries.  Replaces the (D.train, y)

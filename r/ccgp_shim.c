@@ -1,8 +1,12 @@
 /* ccgp_shim.c -- .Call entry points that bind the reference R scripts to libccgp.so.
  *
- * Build (where R exists; R is NOT in the build container, so this file is compile-checked
- * only on a machine with R):
+ * Build (where R exists):
  *     R CMD SHLIB ccgp_shim.c -I../include -L../convex-combination-of-gaussian-processes_b200/lib -lccgp
+ * R is NOT in the build container: there the CPU test suite compiles this file with
+ * `gcc -fsyntax-only -Wall -Wextra -Werror` against the stand-in headers under tests/r_stub/
+ * (tests/test_r_boundary.py), which pins every libccgp call to the prototypes of include/ccgp.h.
+ * Every routine is registered (R_init_ccgp_shim at the end of this file), so `.Call("ccgp_R_...")`
+ * resolves through the registration table, with the argument count checked by R.
  *
  * Conventions: REALSXP matrices are column-major doubles and are handed to libccgp as they
  * are (no copy); INTSXP is int32.  The context handle is an external pointer with a C
@@ -13,6 +17,7 @@
  */
 #include <R.h>
 #include <Rinternals.h>
+#include <R_ext/Rdynload.h>
 #include <stdint.h>
 #include "ccgp.h"
 
@@ -31,14 +36,40 @@ static void check(ccgp_ctx* ctx, int rc, const char* what) {
     if (rc != CCGP_OK) Rf_error("ccgp %s failed (%d): %s", what, rc, ccgp_last_error(ctx));
 }
 
-SEXP ccgp_R_create(SEXP device) {
-    ccgp_ctx* ctx = NULL;
-    int rc = ccgp_create(&ctx, Rf_asInteger(device));
-    if (rc != CCGP_OK) Rf_error("ccgp_create failed (%d): %s", rc, ccgp_last_error(NULL));
+static SEXP wrap_ctx(ccgp_ctx* ctx) {
     SEXP ptr = PROTECT(R_MakeExternalPtr(ctx, R_NilValue, R_NilValue));
     R_RegisterCFinalizerEx(ptr, ctx_finalizer, TRUE);
     UNPROTECT(1);
     return ptr;
+}
+
+SEXP ccgp_R_create(SEXP device) {
+    ccgp_ctx* ctx = NULL;
+    int rc = ccgp_create(&ctx, Rf_asInteger(device));
+    if (rc != CCGP_OK) Rf_error("ccgp_create failed (%d): %s", rc, ccgp_last_error(NULL));
+    return wrap_ctx(ctx);
+}
+
+/* all (n_gpus <= 0) or the first n_gpus GPUs of the box behind one context */
+SEXP ccgp_R_create_multi(SEXP n_gpus) {
+    ccgp_ctx* ctx = NULL;
+    int rc = ccgp_create_multi(&ctx, Rf_asInteger(n_gpus));
+    if (rc != CCGP_OK) Rf_error("ccgp_create_multi failed (%d): %s", rc, ccgp_last_error(NULL));
+    return wrap_ctx(ctx);
+}
+
+SEXP ccgp_R_num_gpus(SEXP ptr) {
+    SEXP out = PROTECT(Rf_allocVector(INTSXP, 1));
+    INTEGER(out)[0] = ccgp_num_gpus(get_ctx(ptr));
+    UNPROTECT(1);
+    return out;
+}
+
+/* Matern smoothness nu of the 1-D families ([D1]:1080) */
+SEXP ccgp_R_set_matern_nu(SEXP ptr, SEXP nu) {
+    ccgp_ctx* ctx = get_ctx(ptr);
+    check(ctx, ccgp_set_matern_nu(ctx, Rf_asReal(nu)), "set_matern_nu");
+    return R_NilValue;
 }
 
 /* D.train (n x d), y (n) */
@@ -183,4 +214,106 @@ SEXP ccgp_R_me_schur_stencil(SEXP ptr, SEXP D_old, SEXP X, SEXP n_new_, SEXP d_,
     UNPROTECT(1);
     check(ctx, rc, "me_schur_stencil");
     return vals;
+}
+
+/* which.min of the batched likelihood (choose.hyperpars' argmax over a sweep is the argmin of -loglik):
+ * returns list(best nll, 1-based index).  On a multi-GPU context the reduction is the NCCL all-reduce. */
+SEXP ccgp_R_nll_argmin(SEXP ptr, SEXP family, SEXP scale, SEXP cand, SEXP sigma2, SEXP mean_mode, SEXP tau) {
+    ccgp_ctx* ctx = get_ctx(ptr);
+    if (!Rf_isMatrix(cand) || !Rf_isReal(cand)) Rf_error("ccgp: candidates must be a double matrix");
+    int64_t B = Rf_nrows(cand), idx = -1;
+    double best = 0.0;
+    int rc = ccgp_nll_argmin(ctx, Rf_asInteger(family), Rf_asInteger(scale), REAL(cand), B, B, Rf_asReal(sigma2),
+                             Rf_asInteger(mean_mode), Rf_asReal(tau), &best, &idx);
+    check(ctx, rc, "nll_argmin");
+    SEXP v = PROTECT(Rf_allocVector(REALSXP, 1));
+    SEXP i = PROTECT(Rf_allocVector(REALSXP, 1));        /* double: B may exceed 2^31 */
+    REAL(v)[0] = best; REAL(i)[0] = (double)(idx + 1);
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 2));
+    SET_VECTOR_ELT(out, 0, v); SET_VECTOR_ELT(out, 1, i);
+    UNPROTECT(3);
+    return out;
+}
+
+/* rcond_1(R) per candidate: the number solve(R) tests against .Machine$double.eps ([A]:448-449).
+ * Returns list(rcond, beta, status). */
+SEXP ccgp_R_rcond_batch(SEXP ptr, SEXP family, SEXP scale, SEXP cand) {
+    ccgp_ctx* ctx = get_ctx(ptr);
+    if (!Rf_isMatrix(cand) || !Rf_isReal(cand)) Rf_error("ccgp: candidates must be a double matrix");
+    int64_t B = Rf_nrows(cand);
+    SEXP rcond = PROTECT(Rf_allocVector(REALSXP, B));
+    SEXP beta = PROTECT(Rf_allocVector(REALSXP, B));
+    SEXP status = PROTECT(Rf_allocVector(INTSXP, B));
+    int rc = ccgp_rcond_batch(ctx, Rf_asInteger(family), Rf_asInteger(scale), REAL(cand), B, B, REAL(rcond), REAL(beta),
+                              (int32_t*)INTEGER(status));
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 3));
+    SET_VECTOR_ELT(out, 0, rcond); SET_VECTOR_ELT(out, 1, beta); SET_VECTOR_ELT(out, 2, status);
+    UNPROTECT(4);
+    check(ctx, rc, "rcond_batch");
+    return out;
+}
+
+/* which.min over the candidate designs of each parameter row ([M]:944-945): returns list(best -det (P), 1-based index (P)). */
+SEXP ccgp_R_me_argmin(SEXP ptr, SEXP D_old, SEXP D_new, SEXP n_new_, SEXP d_, SEXP params) {
+    ccgp_ctx* ctx = get_ctx(ptr);
+    int n_new = Rf_asInteger(n_new_), d = Rf_asInteger(d_);
+    int n_old = Rf_isNull(D_old) ? 0 : Rf_nrows(D_old);
+    int64_t C = Rf_ncols(D_new), P = Rf_nrows(params);
+    SEXP val = PROTECT(Rf_allocVector(REALSXP, P));
+    SEXP idx = PROTECT(Rf_allocVector(REALSXP, P));
+    int64_t* tmp = (int64_t*)R_alloc((size_t)(P > 0 ? P : 1), sizeof(int64_t));
+    int rc = ccgp_me_argmin(ctx, n_old ? REAL(D_old) : NULL, n_old, d, REAL(D_new), n_new, C, REAL(params), P, P, REAL(val), tmp);
+    if (rc == CCGP_OK) for (int64_t q = 0; q < P; ++q) REAL(idx)[q] = (double)(tmp[q] + 1);
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 2));
+    SET_VECTOR_ELT(out, 0, val); SET_VECTOR_ELT(out, 1, idx);
+    UNPROTECT(3);
+    check(ctx, rc, "me_argmin");
+    return out;
+}
+
+/* log det R[S,S] for C index subsets (idx: C x m INTEGER matrix, 1-based) of a pool (N x d): returns list(logdet, status). */
+SEXP ccgp_R_subset_logdet_batch(SEXP ptr, SEXP pool, SEXP idx, SEXP family, SEXP params) {
+    ccgp_ctx* ctx = get_ctx(ptr);
+    if (!Rf_isMatrix(pool) || !Rf_isReal(pool) || !Rf_isMatrix(idx) || !Rf_isInteger(idx)) Rf_error("ccgp: pool must be a double matrix, idx an integer matrix");
+    int64_t N = Rf_nrows(pool), C = Rf_nrows(idx);
+    int d = Rf_ncols(pool), m = Rf_ncols(idx);
+    int32_t* zero = (int32_t*)R_alloc((size_t)(C * m > 0 ? C * m : 1), sizeof(int32_t));
+    for (int64_t e = 0; e < C * m; ++e) zero[e] = INTEGER(idx)[e] - 1;
+    SEXP logdet = PROTECT(Rf_allocVector(REALSXP, C));
+    SEXP status = PROTECT(Rf_allocVector(INTSXP, C));
+    int rc = ccgp_subset_logdet_batch(ctx, REAL(pool), N, d, zero, m, C, C, Rf_asInteger(family), REAL(params), REAL(logdet),
+                                      (int32_t*)INTEGER(status));
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 2));
+    SET_VECTOR_ELT(out, 0, logdet); SET_VECTOR_ELT(out, 1, status);
+    UNPROTECT(3);
+    check(ctx, rc, "subset_logdet_batch");
+    return out;
+}
+
+/* ---- registration --------------------------------------------------------------------------------------- */
+#define CALLDEF(name, n) {#name, (DL_FUNC)&name, n}
+static const R_CallMethodDef ccgp_call_methods[] = {
+    CALLDEF(ccgp_R_create, 1),
+    CALLDEF(ccgp_R_create_multi, 1),
+    CALLDEF(ccgp_R_num_gpus, 1),
+    CALLDEF(ccgp_R_set_matern_nu, 2),
+    CALLDEF(ccgp_R_set_design, 3),
+    CALLDEF(ccgp_R_nll_batch, 7),
+    CALLDEF(ccgp_R_nll_argmin, 7),
+    CALLDEF(ccgp_R_rinv_batch, 5),
+    CALLDEF(ccgp_R_rcond_batch, 4),
+    CALLDEF(ccgp_R_predict, 7),
+    CALLDEF(ccgp_R_me_schur_batch, 6),
+    CALLDEF(ccgp_R_me_argmin, 6),
+    CALLDEF(ccgp_R_me_schur_paired, 7),
+    CALLDEF(ccgp_R_me_schur_stencil, 10),
+    CALLDEF(ccgp_R_subset_logdet_batch, 5),
+    CALLDEF(ccgp_R_mixed_corr, 5),
+    CALLDEF(ccgp_R_kmedoids_pam, 4),
+    {NULL, NULL, 0}
+};
+
+void R_init_ccgp_shim(DllInfo* dll) {
+    R_registerRoutines(dll, NULL, ccgp_call_methods, NULL, NULL);
+    R_useDynamicSymbols(dll, FALSE);
 }

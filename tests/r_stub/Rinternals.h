@@ -39,4 +39,5 @@ void R_ClearExternalPtr(SEXP);
 typedef void (*R_CFinalizer_t)(SEXP);
 void R_RegisterCFinalizerEx(SEXP, R_CFinalizer_t, Rboolean);
 void Rf_error(const char*, ...) __attribute__((noreturn, format(printf, 1, 2)));
+char* R_alloc(size_t, int);
 #endif
