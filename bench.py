@@ -217,13 +217,16 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    _log('engine + inputs ready')
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
+    _log('warm-up done')
     # roofline denominators, measured BEFORE the clock sampler starts (their kernels are not part of the timed region)
     peak = eng.measure_fp64_peak()
     peak_dmma = eng.measure_fp64_peak_dmma()
     barrier()
+    _log('FP64 peaks measured')
     sampler = ClockSampler(local_rank) if rank == 0 else None
     launches0 = eng.launch_count
     barrier()
@@ -251,6 +254,7 @@ def run_ours(args, rank, world, local_rank):
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
     n_bad = int((status != 0).sum().item())
 
+    _log('timed region done')
     # ---- e2e: host buffers through the C-ABI host entry point, copies inside the timed region
     th_f = np.asfortranarray(th_host)
     eng.set_stream(None)
@@ -269,6 +273,7 @@ def run_ours(args, rank, world, local_rank):
     assert np.array_equal(h_nll, nll.cpu().numpy()), "host-pointer path and device path disagree"
     cfg = eng.last_nll_config()
 
+    _log('e2e done')
     # ---- M2: ME subset (Schur) determinants/sec, pool(1000) x params(1000) per step, resident inputs
     me = None
     pred = None
@@ -313,6 +318,7 @@ def run_ours(args, rank, world, local_rank):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             me_e2e_s = float(t.item())
         eng.set_stream(stream.cuda_stream)
+        _log('ME kernel + e2e done')
         me_cpu = None
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
             import multiprocessing as mp
@@ -341,6 +347,7 @@ def run_ours(args, rank, world, local_rank):
               "e2e": {"value": world * 1000 * P * me_steps / me_e2e_s, "unit": "dets/s",
                       "h2d_bytes_per_step": int(1000 * 14 * 8 + P * 24 + 14 * 2 * 8), "d2h_bytes_per_step": int(P * 16),
                       "timed": "wall clock around %d synchronous ccgp_me_argmin host calls (1000 designs x %d rows each)" % (me_steps, P)}}
+        _log('ME cpu baseline done')
         # ---- predictive table (the prediction() stage of the same fit): S posterior rows x T = 625 grid sites, n = 100
         S_p, T_p = 1000, 625
         rng_p = np.random.default_rng(4242 + rank)
@@ -373,6 +380,7 @@ def run_ours(args, rank, world, local_rank):
                 "finite": bool(torch.isfinite(pm).all().item())}
         eng.set_stream(None)
 
+    _log('ME/predict blocks done')
     # ---- strong scaling: ONE batch split over the ranks through the host-pointer call (H2D + kernel + D2H of the rank's
     # slice), then the path's collective -- which.min as two NCCL all-reduces -- INSIDE the timed region.  Three batches:
     # the headline 2^20 stream and the reference's own sweeps ([V]:552-599: 60 x 1728 at n = 14; [H]:549-595: 624 x 1000 at n = 64).
@@ -419,6 +427,7 @@ def run_ours(args, rank, world, local_rank):
                            "which.min of the slice + 2 NCCL all-reduces (MIN value, MIN index of the winners)], max over ranks, best of the repeats")
         eng.set_design(X, y)
 
+    _log('strong block done')
     # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -435,6 +444,7 @@ def run_ours(args, rank, world, local_rank):
                          "dpotrf+dpotri dmnorm), 1 process/core, %s" % (ns, blas_name()),
                "max_rel_err_gpu_vs_cpu": relerr}
 
+    _log('cpu baseline done')
     if rank == 0:
         secs = total_ms * 1e-3
         evals = world * B * args.steps
@@ -498,6 +508,14 @@ def run_ours(args, rank, world, local_rank):
 
 
 _RESULT_FD = None
+_T0 = time.perf_counter()
+
+
+def _log(msg):
+    """progress line on stderr (elapsed wall time since start), rank 0 only"""
+    if int(os.environ.get("RANK", "0")) == 0:
+        sys.stderr.write("[bench %7.1fs] %s\n" % (time.perf_counter() - _T0, msg))
+        sys.stderr.flush()
 
 
 def _emit(line):
