@@ -50,6 +50,7 @@ def parse():
                     help="weak: --batch candidates per GPU (default). strong: ONE --batch-candidate batch split over the ranks, "
                          "the which.min all-reduce inside the timed region; the headline value then is the strong-scaling one")
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling block of the default run")
+    ap.add_argument("--cpu-helper", default=None, help=argparse.SUPPRESS)   # internal: "m1:<in.npy>:<out.npy>" / "me:<in.npz>:<out.npy>"
     return ap.parse_args()
 
 
@@ -95,6 +96,57 @@ class CpuArm:
     def close(self):
         self.pool.close()
         self.pool.join()
+
+
+def cpu_helper(spec):
+    """Internal entry (`--cpu-helper`): the CPU-baseline leg in a FRESH process.  Forking worker pools from the GPU
+    process (CUDA context, NCCL and BLAS threads alive) deadlocked on the GPU box; a new interpreter that never touches
+    CUDA forks its single-threaded-BLAS workers safely.  Prints one JSON line {"dt": seconds, "cores": C}."""
+    kind, fin, fout = spec.split(":")
+    if kind == "m1":
+        th = np.load(fin)
+        arm = CpuArm()
+        arm.run(th[:min(len(th), 256)])
+        dt, ll = arm.run(th)
+        arm.close()
+        np.save(fout, ll)
+        print(json.dumps({"dt": dt, "cores": arm.cores}))
+    else:
+        import multiprocessing as mp
+        z = np.load(fin)
+        D_old, pool, params = z["D_old"], z["pool"], z["params"]
+        cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
+        os.environ["OPENBLAS_NUM_THREADS"] = "1"
+        with mp.get_context("fork").Pool(cores) as pl:
+            pl.map(_cpu_me_worker, [(D_old, pool[:8], params[:1])] * cores)
+            t0 = time.perf_counter()
+            parts = pl.map(_cpu_me_worker, [(D_old, pool, params[i:i + 4]) for i in range(0, len(params), 4)])
+            dt = time.perf_counter() - t0
+        np.save(fout, np.hstack(parts))
+        print(json.dumps({"dt": dt, "cores": cores}))
+
+
+def run_cpu_helper(kind, **arrays):
+    """Run cpu_helper(kind) in a fresh interpreter; returns (seconds, cores, result array) or None on failure."""
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        fin = os.path.join(td, "in.npy" if kind == "m1" else "in.npz")
+        fout = os.path.join(td, "out.npy")
+        if kind == "m1":
+            np.save(fin, arrays["th"])
+        else:
+            np.savez(fin, **arrays)
+        env = dict(os.environ, OPENBLAS_NUM_THREADS="1", CUDA_VISIBLE_DEVICES="")
+        for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+            env.pop(k, None)
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-helper", "%s:%s:%s" % (kind, fin, fout)],
+                               env=env, capture_output=True, text=True, timeout=240)
+            info = json.loads(r.stdout.strip().splitlines()[-1])
+            return info["dt"], info["cores"], np.load(fout)
+        except Exception as ex:  # noqa: BLE001
+            _log("cpu helper %s failed: %r" % (kind, ex))
+            return None
 
 
 def blas_name():
@@ -321,19 +373,15 @@ def run_ours(args, rank, world, local_rank):
         _log('ME kernel + e2e done')
         me_cpu = None
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
-            import multiprocessing as mp
-            cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
-            rows = 4 * cores                                    # 1000 designs x rows parameter rows: a few seconds
-            with mp.get_context("fork").Pool(cores) as pl:
-                pl.map(_cpu_me_worker, [(D_old, pool[:8], params[:1])] * cores)
-                t0 = time.perf_counter()
-                parts = pl.map(_cpu_me_worker, [(D_old, pool, params[i:i + 4]) for i in range(0, rows, 4)])
-                dt = time.perf_counter() - t0
-            nd_cpu = np.hstack(parts)
-            same = bool(np.array_equal(nd_cpu.argmin(axis=0), bi_me[:rows]))
-            me_cpu = {"value": 1000 * rows / dt, "unit": "dets/s", "cores": cores, "kind": "port",
-                      "sample": "1000 designs x first %d parameter rows, oracle Augmented.Mixed.Entropy (cross Grams, solve(R.old) once per row, "
-                                "dgetrf det), 1 process/core" % rows, "argmin_identical_to_gpu": same}
+            ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
+            rows = 4 * ncores                                   # 1000 designs x rows parameter rows: a few seconds
+            got = run_cpu_helper("me", D_old=D_old, pool=pool, params=params[:rows])
+            if got is not None:
+                dt, cores, nd_cpu = got
+                same = bool(np.array_equal(nd_cpu.argmin(axis=0), bi_me[:rows]))
+                me_cpu = {"value": 1000 * rows / dt, "unit": "dets/s", "cores": cores, "kind": "port",
+                          "sample": "1000 designs x first %d parameter rows, oracle Augmented.Mixed.Entropy (cross Grams, solve(R.old) once per row, "
+                                    "dgetrf det), 1 process/core, fresh interpreter" % rows, "argmin_identical_to_gpu": same}
         me = {"metric": "ME subset (Schur) log-dets/sec", "value": world * 1000 * P * me_steps / (me_ms * 1e-3),
               "unit": "dets/s", "workload": "ME-A: Initial ME Design (14x2) + 1000 All_Subdesigns blocks x 1000 parameter rows per GPU per step",
               "ms_per_step": me_ms / me_steps,
@@ -431,18 +479,18 @@ def run_ours(args, rank, world, local_rank):
     # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        arm = CpuArm()
-        ns = args.cpu_sample or max(2048, 2048 * arm.cores // 8 * 1)
+        ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
+        ns = args.cpu_sample or max(2048, 2048 * ncores // 8 * 1)
         ns = min(ns, B)
-        arm.run(th_host[:min(ns, 256)])
-        dt, ll = arm.run(th_host[:ns])
-        arm.close()
-        got = -nll[:ns].cpu().numpy()
-        relerr = float(np.max(np.abs(got - ll) / np.maximum(np.abs(ll), 1.0)))
-        cpu = {"value": ns / dt, "unit": "evals/s", "cores": arm.cores, "kind": "port",
-               "sample": "first %d candidates of the step's batch, reference-faithful oracle path (dgesv+dgecon inverse, "
-                         "dpotrf+dpotri dmnorm), 1 process/core, %s" % (ns, blas_name()),
-               "max_rel_err_gpu_vs_cpu": relerr}
+        got_cpu = run_cpu_helper("m1", th=th_host[:ns])
+        if got_cpu is not None:
+            dt, cores, ll = got_cpu
+            got = -nll[:ns].cpu().numpy()
+            relerr = float(np.max(np.abs(got - ll) / np.maximum(np.abs(ll), 1.0)))
+            cpu = {"value": ns / dt, "unit": "evals/s", "cores": cores, "kind": "port",
+                   "sample": "first %d candidates of the step's batch, reference-faithful oracle path (dgesv+dgecon inverse, "
+                             "dpotrf+dpotri dmnorm), 1 process/core in a fresh interpreter, %s" % (ns, blas_name()),
+                   "max_rel_err_gpu_vs_cpu": relerr}
 
     _log('cpu baseline done')
     if rank == 0:
@@ -538,6 +586,10 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.cpu_helper:
+        os.dup2(_RESULT_FD, 1)
+        cpu_helper(args.cpu_helper)
+        return
     if args.impl == "reference":
         run_reference(args, rank, world)
         return

@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libccgp.so")
+LIB_PATH = os.environ.get("CCGP_LIB_PATH") or os.path.join(_HERE, "lib", "libccgp.so")   # (override: A/B builds during kernel work)
 
 # every symbol include/ccgp.h declares (tests check that the .so exports them all)
 SYMBOLS = [

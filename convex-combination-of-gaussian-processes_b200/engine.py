@@ -7,6 +7,7 @@ engine's stream.  Nothing here computes: every number comes from libccgp.so.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import numpy as np
 
 from . import _capi
@@ -26,6 +27,25 @@ def _ptr(a):
     return None if a is None else a.ctypes.data
 
 
+def _prefer_bundled_nccl():
+    """libccgp.so dlopen()s libnccl.so.2 when a multi-GPU context is created.  In a Python process that later imports
+    torch, the NCCL loaded first wins (same SONAME) and torch's libtorch_cuda.so needs the newer one it ships with
+    (seen on the GPU box: system 2.27.3 loaded first -> `undefined symbol: ncclDevCommCreate` at `import torch`).
+    Point CCGP_NCCL_LIB at the pip-bundled library when there is one; an R process has no such conflict."""
+    if os.environ.get("CCGP_NCCL_LIB"):
+        return
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for root in (spec.submodule_search_locations if spec else []):
+            cand = os.path.join(root, "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                os.environ["CCGP_NCCL_LIB"] = cand
+                return
+    except Exception:  # noqa: BLE001
+        pass
+
+
 class Engine:
     def __init__(self, device: int = 0, n_gpus: int = None):
         """device: one GPU (ccgp_create).  n_gpus: all (<= 0) or the first n GPUs of the box behind one context
@@ -36,6 +56,7 @@ class Engine:
             rc = self._lib.ccgp_create(C.byref(h), int(device))
             what = "ccgp_create(device=%d)" % device
         else:
+            _prefer_bundled_nccl()
             rc = self._lib.ccgp_create_multi(C.byref(h), int(n_gpus))
             what = "ccgp_create_multi(n_gpus=%d)" % n_gpus
         if rc != 0:
