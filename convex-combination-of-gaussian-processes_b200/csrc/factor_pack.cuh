@@ -27,6 +27,13 @@
 
 namespace ccgp {
 
+// the same DMMA as mma884 (factor_mma.cuh), as a volatile statement: the compiler may not move it
+__device__ __forceinline__ void mma884v(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
 constexpr int PACK_LD = 16;                         // leading dimension of the slot table (tile rows)
 constexpr int PACK_MAXNR = 14;
 
@@ -174,11 +181,11 @@ __device__ __forceinline__ void pack_panels(double2 (&cur)[MAXT], const double* 
         for (int t = 0; t < NT; ++t) o[t] = tp[PACK_LD + t];
         const double bx = negd(a[0].x), by = negd(a[0].y);
 #pragma unroll
-        for (int t = 0; t < NT; ++t) mma884(cur[t].x, cur[t].y, a[t].x, bx);
+        for (int t = 0; t < NT; ++t) mma884v(cur[t].x, cur[t].y, a[t].x, bx);
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
-            if (SPLIT) mma884(alt[t].x, alt[t].y, a[t].y, by);
-            else mma884(cur[t].x, cur[t].y, a[t].y, by);
+            if (SPLIT) mma884v(alt[t].x, alt[t].y, a[t].y, by);
+            else mma884v(cur[t].x, cur[t].y, a[t].y, by);
         }
 #pragma unroll
         for (int t = 0; t < NT; ++t) a[t] = an[t];
@@ -194,9 +201,9 @@ template <int NT, int MAXT>
 __device__ __forceinline__ void pack_solve(const double2 (&cur)[MAXT], double2 li, double* Lw, const uint32_t* tabc) {
     double2 x[NT > 1 ? NT : 2];
 #pragma unroll
-    for (int t = 1; t < NT; ++t) { x[t] = make_double2(0.0, 0.0); mma884(x[t].x, x[t].y, cur[t].x, li.x); }
+    for (int t = 1; t < NT; ++t) { x[t] = make_double2(0.0, 0.0); mma884v(x[t].x, x[t].y, cur[t].x, li.x); }
 #pragma unroll
-    for (int t = 1; t < NT; ++t) mma884(x[t].x, x[t].y, cur[t].y, li.y);
+    for (int t = 1; t < NT; ++t) mma884v(x[t].x, x[t].y, cur[t].y, li.y);
 #pragma unroll
     for (int t = 1; t < NT; ++t) st2(Lw + tabc[t], x[t].x, x[t].y);
 }
@@ -269,14 +276,12 @@ __global__ void __launch_bounds__(MAXW * 32, 1) factor_pack_kernel(const FactorA
             if (clamp) pack_build_column<DT, true>(A, Lw, tab + c * PACK_LD, Xs, ys, prm, etab, c, lane, dtile);
             else pack_build_column<DT, false>(A, Lw, tab + c * PACK_LD, Xs, ys, prm, etab, c, lane, dtile);
             CCGP_PT(1);
-            if (A.debug_stop & 2) __syncwarp();
             // the column's tiles into registers (the diagonal tile is already there)
             const uint32_t* tabc = tab + c * PACK_LD + c;      // tabc[t]: tile (c+t, c)
             double2 cur[MAXT];
             cur[0] = dtile;
 #pragma unroll
             for (int t = 1; t < MAXT; ++t) cur[t] = (t < nt) ? ld2(Lw + tabc[t]) : make_double2(0.0, 0.0);
-            if (A.debug_stop & 4) __syncwarp();
             if (c > 0) {
                 switch (nt) {
 #define CCGP_F(NTv) case NTv: if constexpr (NTv <= MAXT) pack_panels<NTv, MAXT>(cur, Lw, tab + c, c); break;
@@ -285,7 +290,6 @@ __global__ void __launch_bounds__(MAXW * 32, 1) factor_pack_kernel(const FactorA
                     default: break;
                 }
             }
-            if (A.debug_stop & 8) __syncwarp();
             // diagonal tile: through shared memory into every lane, factor + inverse (one copy of the routine
             // for all column heights: it is ~1 k instructions, and eight warps at different steps share the
             // instruction cache)

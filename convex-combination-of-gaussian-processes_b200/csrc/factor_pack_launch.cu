@@ -35,7 +35,7 @@ int launch_factor_pack(ccgp_ctx* ctx, FactorArgs& A, int* launched) {
     if (grid < 1) { *launched = 1; return 0; }
     A.team_smem_bytes = (int64_t)wsm;
     A.dbg = ctx->dbg;
-    A.debug_stop = env_int("CCGP_PACK_DEBUG", 0);
+    A.debug_stop = 0;
     A.nparams = (A.family == FAM_ANISO) ? A.d + 2 : 3;
     fn<<<(unsigned)grid, nw * 32, smem, ctx->stream>>>(A);
     CK(cudaGetLastError());
@@ -44,4 +44,5 @@ int launch_factor_pack(ccgp_ctx* ctx, FactorArgs& A, int* launched) {
     *launched = 1;
     return 0;
 }
+
 

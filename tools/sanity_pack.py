@@ -30,11 +30,12 @@ for n, d, logs in cases:
     os.environ.pop("CCGP_KERNEL", None)
     ref, rb, rs = eng.nll_batch(th, GAUSS_ANISO_LAMBDA, s2, scale=scale)
     cfg0 = eng.last_nll_config()["variant"]
-    os.environ["CCGP_KERNEL"] = "5"
-    for rep in range(2):
-        v, b, s = eng.nll_batch(th, GAUSS_ANISO_LAMBDA, s2, scale=scale)
-        ok = np.isfinite(ref) & np.isfinite(v)
-        nbad = int(np.sum(~(np.abs(v - ref) <= 1e-9 * np.abs(ref)) & ~(np.isnan(v) & np.isnan(ref))))
-        print("n=%d d=%d log=%d ref variant %s pack %s: maxrel nll %.2e beta %.2e, NaN sets equal %s, wrong %d of %d (finite %d)" % (
-            n, d, logs, cfg0, eng.last_nll_config(), np.max(np.abs(v[ok] - ref[ok]) / np.maximum(1, np.abs(ref[ok]))),
-            np.max(np.abs(b[ok] - rb[ok]) / np.maximum(1, np.abs(rb[ok]))), np.array_equal(np.isfinite(ref), np.isfinite(v)), nbad, B, ok.sum()))
+    for kern in os.environ.get("SANITY_KERNELS", "5").split(","):
+      os.environ["CCGP_KERNEL"] = kern
+      for rep in range(2):
+          v, b, s = eng.nll_batch(th, GAUSS_ANISO_LAMBDA, s2, scale=scale)
+          ok = np.isfinite(ref) & np.isfinite(v)
+          nbad = int(np.sum(~(np.abs(v - ref) <= 1e-9 * np.abs(ref)) & ~(np.isnan(v) & np.isnan(ref))))
+          print("n=%d d=%d log=%d ref variant %s kernel %s: maxrel nll %.2e beta %.2e, NaN sets equal %s, wrong %d of %d (finite %d)" % (
+              n, d, logs, cfg0, eng.last_nll_config(), np.max(np.abs(v[ok] - ref[ok]) / np.maximum(1, np.abs(ref[ok]))),
+              np.max(np.abs(b[ok] - rb[ok]) / np.maximum(1, np.abs(rb[ok]))), np.array_equal(np.isfinite(ref), np.isfinite(v)), nbad, B, ok.sum()))
