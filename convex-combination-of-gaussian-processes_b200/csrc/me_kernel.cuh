@@ -38,7 +38,8 @@ struct MeArgs {
 };
 
 inline bool me_fast_supported(int n_old, int n_new, int d) {
-    return n_new >= 1 && n_new <= 8 && n_old >= 1 && n_old <= 32 && d >= 1 && d <= 4;
+    // n_old = 0 (the first batch, `Entropy` [M]:856-861): the old block is the identity padding, the cross rows vanish
+    return n_new >= 1 && n_new <= 8 && n_old >= 0 && n_old <= 32 && d >= 1 && d <= 4;
 }
 
 // NOLD: rows of the old design the kernel is unrolled for; DM: coordinates it is unrolled for (d <= DM)

@@ -248,11 +248,14 @@ def entropy_batch(D_old, D_new_pool, params, engine=None):
     return eng.me_schur_batch(D_old, D_new_pool, params)[0]
 
 
-def Batch_Entropy_optim(D_old, n_new, d, p, theta1, theta2, n_starts, rng=None, engine=None, maxiter=200):
+def Batch_Entropy_optim(D_old, n_new, d, p, theta1, theta2, n_starts, rng=None, engine=None, maxiter=100):
     """[M]:920-948: multi-start L-BFGS-B on [-1,1]^(n_new*d); each finite-difference
     gradient is ONE batched GPU call over the 2*n_new*d stencil (optim's ndeps=1e-3
     central differences).  -> dict(Design, log_entropy) with log_entropy = -min.val
-    (a determinant, quirk Q4).  Starts are random LHDs (lhs::optimumLHS stays caller-side)."""
+    (a determinant, quirk Q4).  Starts are random LHDs (lhs::optimumLHS stays caller-side).
+    Stopping rule as the reference's optim call ([M]:936: maxit = 100, pgtol = 0, factr = 1e7) -- the criterion is a
+    tiny determinant, scipy's default gtol = 1e-5 would stop at the start point -- and the difference stencil is
+    clipped to the box like optim's (the step actually taken divides the difference)."""
     from scipy.optimize import minimize
     eng = engine or default_engine()
     rng = rng or np.random.default_rng()
@@ -263,12 +266,14 @@ def Batch_Entropy_optim(D_old, n_new, d, p, theta1, theta2, n_starts, rng=None, 
     def f_and_g(x):
         pts = np.repeat(x[None, :], 2 * m + 1, axis=0)
         h = 1e-3
+        up = np.minimum(x + h, 1.0)
+        dn = np.maximum(x - h, -1.0)
         for i in range(m):
-            pts[1 + 2 * i, i] += h
-            pts[2 + 2 * i, i] -= h
+            pts[1 + 2 * i, i] = up[i]
+            pts[2 + 2 * i, i] = dn[i]
         designs = pts.reshape(-1, d, n_new).transpose(0, 2, 1)   # c(D) is column-major
         nd = eng.me_schur_batch(D_old, designs, par_row)[0][:, 0]
-        g = (nd[1::2] - nd[2::2]) / (2 * h)
+        g = (nd[1::2] - nd[2::2]) / (up - dn)
         return float(nd[0]), g
 
     vals, designs = [], []
@@ -276,14 +281,14 @@ def Batch_Entropy_optim(D_old, n_new, d, p, theta1, theta2, n_starts, rng=None, 
         lhd = (np.argsort(rng.random((n_new, d)), axis=0) + rng.random((n_new, d))) / n_new
         start = (-1.0 + 2.0 * lhd).reshape(-1, order="F")
         res = minimize(f_and_g, start, jac=True, method="L-BFGS-B", bounds=[(-1.0, 1.0)] * m,
-                       options=dict(maxiter=maxiter))
+                       options=dict(maxiter=maxiter, gtol=0.0, ftol=1e7 * np.finfo(float).eps))
         vals.append(res.fun)
         designs.append(res.x.reshape(n_new, d, order="F"))
     k = int(np.argmin(vals))
     return dict(Design=designs[k], log_entropy=-vals[k])
 
 
-def Entropy_optim(n, d, p, theta1, theta2, n_starts, rng=None, engine=None, maxiter=200):
+def Entropy_optim(n, d, p, theta1, theta2, n_starts, rng=None, engine=None, maxiter=100):
     """[M]:886-912: first-batch ME design (no D.old)."""
     return Batch_Entropy_optim(None, n, d, p, theta1, theta2, n_starts, rng, engine, maxiter)
 

@@ -1,13 +1,13 @@
 """Seeded synthetic workloads of SURVEY 8(d), shared by bench.py and tests.
 The designs are the reference's shipped data inputs, read from the committed
-fixture tests/golden/reference_designs.npz (made by tests/golden/make_golden.py)."""
+package data file data/reference_designs.npz (made by tests/golden/make_golden.py from the reference's shipped input files)."""
 from __future__ import annotations
 
 import os
 import numpy as np
 
 _ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-DESIGNS_PATH = os.path.join(_ROOT, "tests", "golden", "reference_designs.npz")
+DESIGNS_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "reference_designs.npz")
 _designs = None
 
 

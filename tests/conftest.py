@@ -20,7 +20,8 @@ def golden():
 
 @pytest.fixture(scope="session")
 def designs():
-    return dict(np.load(os.path.join(ROOT, "tests", "golden", "reference_designs.npz")))
+    from ccgp_b200 import workloads
+    return dict(np.load(workloads.DESIGNS_PATH))
 
 
 @pytest.fixture(scope="session")

@@ -88,7 +88,7 @@ def nll_case(X, y, sigma2, family, nat, mean_mode, tau, n_truth):
 
 def main():
     D = designs()
-    np.savez_compressed(os.path.join(OUT, "reference_designs.npz"), **D)
+    np.savez_compressed(os.path.join(os.path.dirname(os.path.dirname(OUT)), "convex-combination-of-gaussian-processes_b200", "data", "reference_designs.npz"), **D)
     G = {}
 
     # ---- C1: n=100 aniso, bench distribution (SURVEY 8d M1 primary) -------------

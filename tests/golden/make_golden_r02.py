@@ -52,7 +52,7 @@ def _me_rows(args):
 
 
 def main():
-    D = dict(np.load(os.path.join(OUT, "reference_designs.npz")))
+    D = dict(np.load(os.path.join(os.path.dirname(os.path.dirname(OUT)), "convex-combination-of-gaussian-processes_b200", "data", "reference_designs.npz")))
     GV = gv_sets()
     np.savez_compressed(os.path.join(OUT, "gv_sets.npz"), **GV)
     G = {}

@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, ccgp_b200, time
 from ccgp_b200 import me_design
 from scipy.optimize import minimize
-z=np.load("tests/golden/reference_designs.npz"); D_old=z["me_initial14"]
+z=np.load("convex-combination-of-gaussian-processes_b200/data/reference_designs.npz"); D_old=z["me_initial14"]
 e=ccgp_b200.Engine(0); rng=np.random.default_rng(11)
 P=8; params=np.column_stack([rng.uniform(0.3,0.7,P), rng.uniform(0.5,2.0,P), rng.uniform(3.0,6.0,P)])
 ns=10

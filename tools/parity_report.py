@@ -15,7 +15,7 @@ from ccgp_b200 import reference_api as api  # noqa: E402
 
 G = dict(np.load(os.path.join(ROOT, "tests", "golden", "golden_cases.npz")))
 G2 = dict(np.load(os.path.join(ROOT, "tests", "golden", "golden_r02.npz")))
-D = dict(np.load(os.path.join(ROOT, "tests", "golden", "reference_designs.npz")))
+D = dict(np.load(os.path.join(ROOT, "convex-combination-of-gaussian-processes_b200", "data", "reference_designs.npz")))
 GV = dict(np.load(os.path.join(ROOT, "tests", "golden", "gv_sets.npz")))
 
 
