@@ -14,9 +14,9 @@ import ccgp_b200  # noqa: E402
 from ccgp_b200 import reference_api as api, samplers, workloads  # noqa: E402
 
 
-def fit(eng, C, seed=1, N=5000, samp_size=1000, batch_size=20, alpha=0.5):
+def fit(eng, C, seed=1, N=5000, samp_size=1000, batch_size=20, alpha=0.5, train=None, test=None):
     D = workloads.designs()
-    tr, te = D["gv50_train1"], D["gv50_test1"]
+    tr, te = (D["gv50_train1"], D["gv50_test1"]) if train is None else (train, test)
     X, y = tr[:, :9], tr[:, 9]
     sigma2 = float(np.var(y, ddof=1))                       # stand-in for mlegp(D.train, y.train)$sig2 ([G]:720-721)
     fn = lambda th: api.logpost_batch(X, th, y, sigma2, script="G", engine=eng)   # noqa: E731
