@@ -17,6 +17,7 @@ SYMBOLS = [
     "ccgp_subset_logdet_batch", "ccgp_subset_logdet_batch_dev", "ccgp_mixed_corr", "ccgp_debug_phase_timing",
     "ccgp_kmedoids_pam", "ccgp_me_schur_paired", "ccgp_me_schur_stencil", "ccgp_rcond_batch",
     "ccgp_create_multi", "ccgp_num_gpus", "ccgp_collective_count", "ccgp_measure_fp64_peak_dmma",
+    "ccgp_cgp_objective_batch", "ccgp_cgp_jackknife",
 ]
 
 _lib = None
@@ -79,6 +80,8 @@ def load():
     lib.ccgp_me_schur_paired.argtypes = [vp, dp, i32, i32, dp, i32, i64, dp, i64, i64, dp, ip]
     lib.ccgp_me_schur_stencil.argtypes = [vp, dp, i32, i32, dp, i32, i64, dp, i64, i64, f64, f64, f64, dp, ip]
     lib.ccgp_kmedoids_pam.argtypes = [vp, dp, i64, i32, i32, i32, ip, dp, ip]
+    lib.ccgp_cgp_objective_batch.argtypes = [vp, dp, dp, i32, i32, dp, i64, i64, dp, ip]
+    lib.ccgp_cgp_jackknife.argtypes = [vp, dp, dp, i32, i32, dp, dp, ip]
     for s in SYMBOLS:
         fn = getattr(lib, s)
         if s not in ("ccgp_last_error", "ccgp_launch_count", "ccgp_collective_count"):

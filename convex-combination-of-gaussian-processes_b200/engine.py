@@ -332,6 +332,32 @@ class Engine:
         self._ck(self._lib.ccgp_kmedoids_pam(self._h, _ptr(P), n, d, int(k), int(max_swaps), _ptr(med), _ptr(cost), _ptr(swaps)))
         return med, float(cost[0]), int(swaps[0])
 
+    def cgp_objective_batch(self, Xs, y, W):
+        """CGP comparator: var.MLE.DK ([A]:104-135) for the rows (lambda, theta_1..p, kappa, bw) of W on the standardised
+        design Xs -> (values[B], status[B])."""
+        Xs = _f(np.atleast_2d(Xs))
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        W = _f(np.atleast_2d(W))
+        n, p = Xs.shape
+        B = W.shape[0]
+        assert W.shape[1] == p + 3 and y.shape[0] == n
+        out = np.empty(B)
+        st = np.zeros(B, dtype=np.int32)
+        self._ck(self._lib.ccgp_cgp_objective_batch(self._h, _ptr(Xs), _ptr(y), n, p, _ptr(W), B, B, _ptr(out), _ptr(st)))
+        return out, st
+
+    def cgp_jackknife(self, Xs, y, w):
+        """CGP comparator: Yp_jackknife ([A]:166-199) for ONE parameter row w -> (predictions[n], status[n])."""
+        Xs = _f(np.atleast_2d(Xs))
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        w = np.ascontiguousarray(np.asarray(w, dtype=np.float64).reshape(-1))
+        n, p = Xs.shape
+        assert w.shape[0] == p + 3 and y.shape[0] == n
+        out = np.empty(n)
+        st = np.zeros(n, dtype=np.int32)
+        self._ck(self._lib.ccgp_cgp_jackknife(self._h, _ptr(Xs), _ptr(y), n, p, _ptr(w), _ptr(out), _ptr(st)))
+        return out, st
+
     def mixed_corr(self, params, family, A, B=None):
         """Mixed correlation block between the rows of A and of B (B=None: A with itself)."""
         A = _f(np.atleast_2d(A))

@@ -303,3 +303,56 @@ def kmedoids_design(D_old, subdesigns, k, engine=None):
     med, cost, _ = eng.kmedoids_pam(P, k)
     D_old = np.atleast_2d(np.asarray(D_old, dtype=np.float64))
     return dict(Design=np.vstack([D_old, P[med]]), medoid_rows=med, cost=cost)
+
+
+# ---- CGP comparator (SURVEY 8f rank 4): the start sweep and the leave-one-out loop of `CGP` ([A]:60-237) ----------
+def cgp_standardise(X):
+    """[A]:70-72: per column (x - min) / (max - min) and the scales max - min."""
+    X = np.atleast_2d(np.asarray(X, dtype=np.float64))
+    lo = X.min(axis=0)
+    scales = X.max(axis=0) - lo
+    return (X - lo) / scales, scales
+
+
+def cgp_bounds(X, nugget_l=0.001, theta_l=1e-4):
+    """[A]:79-92: the box (lower, upper) of (lambda, theta_1..p, kappa, bw) the sweep and optim's L-BFGS-B use."""
+    Xs, _ = cgp_standardise(X)
+    n, p = Xs.shape
+    iu = np.triu_indices(n, 1)
+    d2 = ((Xs[:, None, :] - Xs[None, :, :]) ** 2).sum(axis=2)[iu]
+    m = np.mean(1.0 / d2)
+    alpha_l, kappa_u = np.log(10.0 ** 2) * m, np.log(10.0 ** 6) * m
+    return (np.concatenate([[nugget_l], np.full(p, theta_l), [alpha_l, 0.0]]),
+            np.concatenate([[1.0], np.full(p, alpha_l), [kappa_u, 1.0]]))
+
+
+def cgp_start_candidates(X, num_starts=5, rng=None):
+    """[A]:137-147: the (500 + num_starts) x (p + 3) random Latin hypercube of start candidates, scaled to the box."""
+    rng = rng or np.random.default_rng()
+    lower, upper = cgp_bounds(X)
+    N, k = 500 + num_starts, len(lower)
+    lhd = (np.column_stack([rng.permutation(N) + 1 for _ in range(k)]) - 0.5) / N
+    return lhd * (upper - lower) + lower
+
+
+def var_MLE_DK_batch(X, yobs, starts, engine=None):
+    """`apply(starts, 1, var.MLE.DK)` ([A]:148) in one launch -> cand_obj."""
+    eng = engine or default_engine()
+    Xs, _ = cgp_standardise(X)
+    return eng.cgp_objective_batch(Xs, np.asarray(yobs, dtype=np.float64), starts)[0]
+
+
+def cgp_best_starts(X, yobs, starts, num_starts=5, engine=None):
+    """[A]:148-150: the rows whose objective ranks among the num_starts smallest (rank(.., ties = "min") <= num_starts)."""
+    obj = var_MLE_DK_batch(X, yobs, starts, engine)
+    rank = np.array([1 + np.sum(obj < v) for v in obj])
+    return np.asarray(starts)[rank <= num_starts], obj
+
+
+def cgp_jackknife(X, yobs, par, engine=None):
+    """Yp_jackknife and rmscv ([A]:166-201) for the fitted row par = op$par (lambda, Stand_theta, kappa, bw)."""
+    eng = engine or default_engine()
+    Xs, _ = cgp_standardise(X)
+    yobs = np.asarray(yobs, dtype=np.float64)
+    yp = eng.cgp_jackknife(Xs, yobs, par)[0]
+    return dict(Yp_jackknife=yp, rmscv=float(np.sqrt(np.sum((yobs - yp) ** 2) / len(yobs))))

@@ -203,6 +203,19 @@ int ccgp_me_argmin(ccgp_ctx* ctx, const double* D_old, int n_old, int d,
 int ccgp_kmedoids_pam(ccgp_ctx* ctx, const double* P, int64_t n, int d, int k, int max_swaps,
                       int32_t* out_medoids, double* out_cost, int32_t* out_swaps);
 
+/* CGP comparator (the composite GP every reference script re-states, [A]:60-319 = "2D Combined GP
+ * Anisotropic Public.R").  Xs: n x p column-major design STANDARDISED to [0,1] per column ([A]:70); W: B parameter
+ * rows (lambda, theta_1..theta_p, kappa, bw), column-major with leading dimension ldw.
+ * ccgp_cgp_objective_batch replaces `apply(starts, 1, var.MLE.DK)` ([A]:104-135, 148): out_val[b] = log(det(Q)) +
+ *   n log(tau2) after the four re-weighting passes, 1e6 where the reference's value is not finite.
+ * ccgp_cgp_jackknife replaces the leave-one-out loop ([A]:166-199) for ONE parameter row w[p+3]:
+ *   out_yp[jf] = Yp_jackknife[jf].  (theta = Stand_theta / scales^2 on the raw design, [A]:164-165, is the same
+ *   correlation as Stand_theta on the standardised one.)  out_status (may be NULL): 1 = a pivot of Q was not positive. */
+int ccgp_cgp_objective_batch(ccgp_ctx* ctx, const double* Xs, const double* y, int n, int p, const double* W, int64_t B,
+                             int64_t ldw, double* out_val, int32_t* out_status);
+int ccgp_cgp_jackknife(ccgp_ctx* ctx, const double* Xs, const double* y, int n, int p, const double* w, double* out_yp,
+                       int32_t* out_status);
+
 /* log det R[S,S] for C index subsets (0-based, C x m column-major, ldi >= C) of a
  * pool of N points (N x d column-major): the ME subset log-dets of the scaling
  * case.  One natural-scale parameter row of `family`. */

@@ -638,3 +638,103 @@ def pam_kmedoids(P, k, max_swaps=1000, trace=None):
             trace.append(("swap", best[1], best[2]))
     cost = D[:, med].min(axis=1).sum()
     return np.array(med, dtype=np.int32), float(cost), swaps
+
+
+# ------------------------------------------------------------------------------------------------------------
+# CGP comparator (Ba & Joseph's composite GP as re-stated in every script, SURVEY 8f rank 4): the objective of
+# its 505-candidate start sweep and the leave-one-out loop.  Literal restatement of [A]:93-200
+# ("2D Combined GP Anisotropic Public.R"; the same text sits in all eight scripts).
+def cgp_standardise(X):
+    """[A]:70-72: Stand_DD = (x - min) / (max - min) per column; scales = max - min."""
+    X = np.atleast_2d(np.asarray(X, dtype=np.float64))
+    lo = X.min(axis=0)
+    scales = X.max(axis=0) - lo
+    return (X - lo) / scales, scales
+
+
+def cgp_psi(Xs, theta):
+    """PSI / Stand_PSI [A]:93-104: exp(-dist(X diag(sqrt(theta)))^2) -- `dist` is the Euclidean distance, squared again."""
+    A = Xs * np.sqrt(np.asarray(theta, dtype=np.float64))[None, :]
+    D = np.sqrt(((A[:, None, :] - A[None, :, :]) ** 2).sum(axis=2))
+    return np.exp(-D ** 2)
+
+
+def cgp_bounds(Xs, nugget_l=0.001, theta_l=1e-4):
+    """[A]:79-92: lower / upper box of (lambda, theta_1..theta_p, kappa, bw)."""
+    n, p = Xs.shape
+    iu = np.triu_indices(n, 1)
+    d = np.sqrt(((Xs[:, None, :] - Xs[None, :, :]) ** 2).sum(axis=2))[iu]
+    m = np.mean(1.0 / d ** 2)
+    alpha_l = np.log(10.0 ** 2) * m
+    kappa_u = np.log(10.0 ** 6) * m
+    lower = np.concatenate([[nugget_l], np.full(p, theta_l), [alpha_l, 0.0]])
+    upper = np.concatenate([[1.0], np.full(p, alpha_l), [kappa_u, 1.0]])
+    return lower, upper
+
+
+def _cgp_iterate(G, L, Gbw, y, lam, reps=4):
+    """The four re-weighting passes shared by var.MLE.DK ([A]:113-124), the jackknife ([A]:172-183) and the final
+    fit ([A]:206-217).  Returns (Sig diagonal, Sig2 of the last pass, e of the last pass)."""
+    n = len(y)
+    one = np.ones(n)
+    sig = np.ones(n)
+    sig2 = 1.0
+    e = np.zeros(n)
+    for _ in range(reps):
+        Q = G + lam * (np.sqrt(sig)[:, None] * L * np.sqrt(sig)[None, :])
+        invQ = r_solve(Q, tol=EPS)
+        beta = (one @ invQ @ y) / (one @ invQ @ one)
+        temp = invQ @ (y - beta * one)
+        gip = beta * one + G @ temp
+        e = y - gip
+        sig = (Gbw @ e ** 2) / (Gbw @ one)
+        sig2 = float(np.mean(sig))
+        sig = sig / sig2
+    return sig, sig2, e
+
+
+def cgp_var_mle_dk(Xs, y, ww):
+    """var.MLE.DK(ww) [A]:104-135 on the standardised design: log(det(Q)) + n log(tau2), 1e6 when not finite
+    (det underflows to 0 -> log = -Inf -> 1e6: reproduced by going through det itself)."""
+    Xs = np.atleast_2d(Xs)
+    y = np.asarray(y, dtype=np.float64)
+    n, p = Xs.shape
+    ww = np.asarray(ww, dtype=np.float64)
+    lam, th, kappa, bw = ww[0], ww[1:p + 1], ww[p + 1], ww[p + 2]
+    G, L, Gbw = cgp_psi(Xs, th), cgp_psi(Xs, kappa + th), cgp_psi(Xs, th * bw)
+    one = np.ones(n)
+    try:
+        sig, _, _ = _cgp_iterate(G, L, Gbw, y, lam)
+        Q = G + lam * (np.sqrt(sig)[:, None] * L * np.sqrt(sig)[None, :])
+        invQ = r_solve(Q, tol=EPS)
+        beta = (one @ invQ @ y) / (one @ invQ @ one)
+        tau2 = (y - beta * one) @ invQ @ (y - beta * one) / n
+        with np.errstate(divide="ignore", invalid="ignore"):
+            val = float(np.log(r_det(Q)) + n * np.log(tau2))
+    except Exception:  # noqa: BLE001  (solve() refusing a singular Q stops the R function; the sweep never sees it in practice)
+        val = float("nan")
+    return val if np.isfinite(val) else 1e6
+
+
+def cgp_jackknife(X, y, lam, theta, alpha, bw):
+    """Leave-one-out predictions Yp_jackknife and rmscv ([A]:166-201) on the ORIGINAL coordinates with
+    theta = Stand_theta / scales^2, alpha = Stand_alpha / scales^2 ([A]:164-165)."""
+    X = np.atleast_2d(np.asarray(X, dtype=np.float64))
+    y = np.asarray(y, dtype=np.float64)
+    n = X.shape[0]
+    Gf, Lf, Gbwf = cgp_psi(X, theta), cgp_psi(X, alpha), cgp_psi(X, np.asarray(theta) * bw)
+    out = np.zeros(n)
+    for jf in range(n):
+        keep = np.arange(n) != jf
+        G, L, Gbw, yk = Gf[np.ix_(keep, keep)], Lf[np.ix_(keep, keep)], Gbwf[np.ix_(keep, keep)], y[keep]
+        onem = np.ones(n - 1)
+        sig, sig2, e = _cgp_iterate(G, L, Gbw, yk, lam)
+        Q = G + lam * (np.sqrt(sig)[:, None] * L * np.sqrt(sig)[None, :])
+        invQ = r_solve(Q, tol=EPS)
+        beta = (onem @ invQ @ yk) / (onem @ invQ @ onem)
+        temp = invQ @ (yk - beta * onem)
+        g, l, gbw = Gf[jf, keep], Lf[jf, keep], Gbwf[jf, keep]
+        vjf = ((gbw @ e ** 2) / (gbw @ onem)) / sig2
+        q = g + lam * np.sqrt(vjf) * (np.sqrt(sig) * l)
+        out[jf] = beta + q @ temp
+    return out, float(np.sqrt(np.sum((y - out) ** 2) / n))

@@ -317,3 +317,15 @@ kmedoids.design <- function(D.old, subdesigns, k) {
   r <- .Call("ccgp_R_kmedoids_pam", .ccgp$ctx, P, as.integer(k), 1000L)   # list(medoid rows (1-based), cost, swaps)
   list(Design = rbind(as.matrix(D.old), P[r[[1]], , drop = FALSE]), medoid.rows = r[[1]], cost = r[[2]])
 }
+
+# ---- CGP comparator ([A]:60-237): the 505-candidate start sweep and the leave-one-out loop on the device ----------
+# Inside the reference's CGP() the two lines to swap are
+#   cand_obj <- apply(starts, 1, var.MLE.DK)                        ([A]:148)  ->  var.MLE.DK.batch(DD, yobs, starts)
+#   for (jf in 1:n) { ... Yjfp[jf] <- beta + t(q) %*% temp }        ([A]:166-199) ->  Yjfp <- cgp.jackknife(DD, yobs, op$par)
+# (optim's own calls of var.MLE.DK, [A]:151-156, stay scalar R: they are sequential line searches.)
+.ccgp.standardise <- function(X) apply(as.matrix(X), 2, function(x) (x - min(x)) / max(x - min(x)))     # [A]:70
+var.MLE.DK.batch <- function(X, yobs, starts)
+  .Call("ccgp_R_cgp_objective_batch", .ccgp$ctx, matrix(as.double(.ccgp.standardise(X)), nrow = nrow(X)), as.double(yobs),
+        matrix(as.double(starts), nrow = nrow(starts)))
+cgp.jackknife <- function(X, yobs, par)
+  .Call("ccgp_R_cgp_jackknife", .ccgp$ctx, matrix(as.double(.ccgp.standardise(X)), nrow = nrow(X)), as.double(yobs), as.double(par))

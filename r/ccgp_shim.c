@@ -292,6 +292,29 @@ SEXP ccgp_R_subset_logdet_batch(SEXP ptr, SEXP pool, SEXP idx, SEXP family, SEXP
 
 /* ---- registration --------------------------------------------------------------------------------------- */
 #define CALLDEF(name, n) {#name, (DL_FUNC)&name, n}
+/* CGP comparator ([A]:104-151, 166-199): objective of the start sweep / leave-one-out predictions */
+SEXP ccgp_R_cgp_objective_batch(SEXP ptr, SEXP Xs, SEXP y, SEXP W) {
+    ccgp_ctx* ctx = get_ctx(ptr);
+    int n = Rf_nrows(Xs), p = Rf_ncols(Xs);
+    int64_t B = Rf_nrows(W);
+    if (Rf_ncols(W) != p + 3 || XLENGTH(y) != (R_xlen_t)n) Rf_error("ccgp: W needs ncol(Xs) + 3 columns and y nrow(Xs) entries");
+    SEXP out = PROTECT(Rf_allocVector(REALSXP, B));
+    int rc = ccgp_cgp_objective_batch(ctx, REAL(Xs), REAL(y), n, p, REAL(W), B, B, REAL(out), NULL);
+    UNPROTECT(1);
+    check(ctx, rc, "cgp_objective_batch");
+    return out;
+}
+SEXP ccgp_R_cgp_jackknife(SEXP ptr, SEXP Xs, SEXP y, SEXP w) {
+    ccgp_ctx* ctx = get_ctx(ptr);
+    int n = Rf_nrows(Xs), p = Rf_ncols(Xs);
+    if (XLENGTH(w) != (R_xlen_t)(p + 3) || XLENGTH(y) != (R_xlen_t)n) Rf_error("ccgp: w needs ncol(Xs) + 3 entries and y nrow(Xs) entries");
+    SEXP out = PROTECT(Rf_allocVector(REALSXP, n));
+    int rc = ccgp_cgp_jackknife(ctx, REAL(Xs), REAL(y), n, p, REAL(w), REAL(out), NULL);
+    UNPROTECT(1);
+    check(ctx, rc, "cgp_jackknife");
+    return out;
+}
+
 static const R_CallMethodDef ccgp_call_methods[] = {
     CALLDEF(ccgp_R_create, 1),
     CALLDEF(ccgp_R_create_multi, 1),
@@ -310,6 +333,8 @@ static const R_CallMethodDef ccgp_call_methods[] = {
     CALLDEF(ccgp_R_subset_logdet_batch, 5),
     CALLDEF(ccgp_R_mixed_corr, 5),
     CALLDEF(ccgp_R_kmedoids_pam, 4),
+    CALLDEF(ccgp_R_cgp_objective_batch, 4),
+    CALLDEF(ccgp_R_cgp_jackknife, 4),
     {NULL, NULL, 0}
 };
 

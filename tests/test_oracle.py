@@ -133,3 +133,33 @@ def test_expanded_square_form_is_what_r_computes():
     R = orc.corr_matrix(X, [3.0, 5.0])
     Rd = orc.Mixed_corr_matrix_direct(X, orc.FAMILY_ANISO_LAMBDA, [1.0, 3.0, 5.0, 0.0])
     assert np.abs(R - Rd).max() < 1e-13
+
+
+def test_cgp_objective_restatement_against_a_cholesky_formulation(designs):
+    """CGP comparator ([A]:104-135): the literal restatement (LU inverse, det) against the same objective written with
+    a Cholesky factor -- two independent codings of one formula."""
+    from ccgp_b200 import workloads
+    X = designs["maximin14"]
+    y = workloads.test_function_4(X)
+    Xs, _ = orc.cgp_standardise(X)
+    lower, upper = orc.cgp_bounds(Xs)
+    assert lower[0] == 0.001 and upper[0] == 1.0 and lower[-1] == 0.0 and upper[-1] == 1.0
+    assert np.isclose(upper[1], lower[3]) and np.isclose(upper[3] / lower[3], 3.0)        # alpha_l, kappa_u = 3 alpha_l
+    rng = np.random.default_rng(3)
+    for w in lower + (upper - lower) * rng.random((12, 5)):
+        lam, th, kappa, bw = w[0], w[1:3], w[3], w[4]
+        G, L, Gbw = orc.cgp_psi(Xs, th), orc.cgp_psi(Xs, kappa + th), orc.cgp_psi(Xs, th * bw)
+        n, one, sig = 14, np.ones(14), np.ones(14)
+        for rep in range(5):
+            Q = G + lam * np.sqrt(np.outer(sig, sig)) * L
+            C = np.linalg.cholesky(Q)
+            uy, u1 = np.linalg.solve(C.T, np.linalg.solve(C, y)), np.linalg.solve(C.T, np.linalg.solve(C, one))
+            beta = uy.sum() / u1.sum()
+            temp = uy - beta * u1
+            if rep == 4:
+                break
+            e = y - beta - G @ temp
+            sig = (Gbw @ e ** 2) / (Gbw @ one)
+            sig = sig / sig.mean()
+        val = 2.0 * np.log(np.diag(C)).sum() + n * np.log((y - beta) @ temp / n)
+        assert abs(orc.cgp_var_mle_dk(Xs, y, w) - val) < 1e-7 * max(1.0, abs(val))
