@@ -263,19 +263,22 @@ __device__ __forceinline__ void cp_async16(double* dst_smem, const double* src) 
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
 }
 // TRSM = true: rows below the diagonal block of column k, X = A inv(L_kk)' (K = 64, B operand = G.linv), in place.
+// chlo, chhi: the 32-column chunks of the contraction this launch covers (update mode: panels chlo/2 .. chhi/2 - 1 -- the
+// lookahead splits a column's update into "everything but the last panel", launched early on a side stream, and the last
+// panel; TRSM mode: 0, 2).
 template <bool TRSM>
-__global__ void __launch_bounds__(256, 2) big_update_kernel(BigArgs G, int k) {
+__global__ void __launch_bounds__(256, 2) big_update_kernel(BigArgs G, int k, int chlo, int chhi) {
     extern __shared__ __align__(16) double sm[];
     const int b = blockIdx.y, tid = threadIdx.x;
     const int row0 = (TRSM ? (k + 1) * 64 : k * 64) + blockIdx.x * 128;   // first row of this tile
     const int rows_here = min(128, G.nrp - row0);                     // 128 or 64
     const double* Ab = G.A + (size_t)b * G.stride;
-    const int nch = TRSM ? 2 : 2 * k;                                 // 32-column chunks: panels 0..k-1, or block column k itself
+    const int nch = chhi - chlo;                                      // 32-column chunks: panels of the range, or block column k itself
     const double* Lt = G.linv + (size_t)b * 4096;
     auto load = [&](int stage, int ch) {
         double* As = sm + stage * BU_STAGE;
         double* Bs = As + BU_KC * BU_LDA;
-        const size_t col0 = (size_t)ch * BU_KC + (TRSM ? (size_t)k * 64 : 0);
+        const size_t col0 = (size_t)(chlo + ch) * BU_KC + (TRSM ? (size_t)k * 64 : 0);
         for (int e = tid; e < BU_KC * 64; e += 256) {                 // A: 32 columns x 64 chunks of 2 rows
             const int kk = e >> 6, r2 = (e & 63) * 2;
             double* dst = As + kk * BU_LDA + r2;
@@ -434,17 +437,37 @@ inline int bigchol_nll_batch(BigCholWorkspace& ws, cudaStream_t stream, int num_
         big_build_kernel<<<dim3(T, T + 1, nb), 256, 0, stream>>>(G);
         *launches += 2;
         const bool right_looking = getenv("CCGP_BIG_RIGHT") && atoi(getenv("CCGP_BIG_RIGHT"));   // the old schedule, for A/B runs
+        // Lookahead (left-looking): column k's update = panels 0..k-1.  Everything but the last panel only needs columns
+        // <= k-2, so it is launched on a side stream as soon as column k-2 is final and overlaps the short serial kernels of
+        // column k-1 (last-panel update, 64x64 factor + inverse on nb CTAs, solve); the main stream then adds panel k-1.
+        const bool lookahead = !right_looking && !(getenv("CCGP_BIG_LOOKAHEAD") && !atoi(getenv("CCGP_BIG_LOOKAHEAD")));
+        if (lookahead && !ws.side) {
+            BIGCK(cudaStreamCreateWithFlags(&ws.side, cudaStreamNonBlocking));
+            BIGCK(cudaEventCreateWithFlags(&ws.ev_main, cudaEventDisableTiming));
+            BIGCK(cudaEventCreateWithFlags(&ws.ev_side[0], cudaEventDisableTiming));
+            BIGCK(cudaEventCreateWithFlags(&ws.ev_side[1], cudaEventDisableTiming));
+        }
         for (int k = 0; k < T; ++k) {
             if (!right_looking && k > 0) {
                 const int nrt = (nrp - k * 64 + 127) / 128;
-                big_update_kernel<false><<<dim3(nrt, nb), 256, 2 * BU_STAGE * 8, stream>>>(G, k);
+                const bool split = lookahead && k >= 2;
+                if (split) BIGCK(cudaStreamWaitEvent(stream, ws.ev_side[k & 1], 0));   // panels 0..k-2 are in (side stream)
+                big_update_kernel<false><<<dim3(nrt, nb), 256, 2 * BU_STAGE * 8, stream>>>(G, k, split ? 2 * (k - 1) : 0, 2 * k);
                 *launches += 1;
             }
             big_potrf_kernel<<<nb, 256, 0, stream>>>(G, k);
             const int rt = (nrp - (k + 1) * 64) / 64;           // row tiles below the diagonal block
             if (rt > 0 && right_looking) big_trsm_kernel<<<dim3(rt, nb), 64, 2 * 64 * 65 * 8, stream>>>(G, k);
-            else if (rt > 0) big_update_kernel<true><<<dim3((rt * 64 + 127) / 128, nb), 256, 2 * BU_STAGE * 8, stream>>>(G, k);
+            else if (rt > 0) big_update_kernel<true><<<dim3((rt * 64 + 127) / 128, nb), 256, 2 * BU_STAGE * 8, stream>>>(G, k, 0, 2);
             *launches += 2;
+            if (lookahead && k + 2 < T) {                       // column k is final: panels 0..k of column k+2, on the side
+                BIGCK(cudaEventRecord(ws.ev_main, stream));
+                BIGCK(cudaStreamWaitEvent(ws.side, ws.ev_main, 0));
+                const int nrt2 = (nrp - (k + 2) * 64 + 127) / 128;
+                big_update_kernel<false><<<dim3(nrt2, nb), 256, 2 * BU_STAGE * 8, ws.side>>>(G, k + 2, 0, 2 * (k + 1));
+                BIGCK(cudaEventRecord(ws.ev_side[k & 1], ws.side));             // (k + 2) & 1: waited on at step k + 2, re-recorded after that wait
+                *launches += 1;
+            }
             const int ct = T - (k + 1);                         // real block columns still to update
             if (right_looking && ct > 0) {
                 // tiles (ti, tj) with tj < ct, ti in [tj, rt): sum_{tj<ct} (rt - tj)

@@ -13,12 +13,18 @@ struct BigCholWorkspace {
     double* linv = nullptr;    // chunk * 64 * 64: inverse of the current diagonal block, transposed (k-major B operand)
     size_t bytesA = 0;
     int cap = 0;
+    cudaStream_t side = nullptr;          // lookahead: the bulk of the NEXT block column's update runs here (bigchol.cuh)
+    cudaEvent_t ev_main = nullptr, ev_side[2] = {nullptr, nullptr};   // ev_side[k & 1]: the early part of column k is in
     void release() {
         if (A) cudaFree(A);
         if (logdet) cudaFree(logdet);
         if (bad) cudaFree(bad);
         if (prm) cudaFree(prm);
         if (linv) cudaFree(linv);
+        if (side) cudaStreamDestroy(side);
+        if (ev_main) cudaEventDestroy(ev_main);
+        for (int i = 0; i < 2; ++i) { if (ev_side[i]) cudaEventDestroy(ev_side[i]); ev_side[i] = nullptr; }
+        side = nullptr; ev_main = nullptr;
         A = nullptr; logdet = nullptr; bad = nullptr; prm = nullptr; linv = nullptr; bytesA = 0; cap = 0;
     }
 };
