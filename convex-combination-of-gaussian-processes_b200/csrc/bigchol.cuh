@@ -438,34 +438,46 @@ inline int bigchol_nll_batch(BigCholWorkspace& ws, cudaStream_t stream, int num_
         *launches += 2;
         const bool right_looking = getenv("CCGP_BIG_RIGHT") && atoi(getenv("CCGP_BIG_RIGHT"));   // the old schedule, for A/B runs
         // Lookahead (left-looking): column k's update = panels 0..k-1.  Everything but the last panel only needs columns
-        // <= k-2, so it is launched on a side stream as soon as column k-2 is final and overlaps the short serial kernels of
-        // column k-1 (last-panel update, 64x64 factor + inverse on nb CTAs, solve); the main stream then adds panel k-1.
-        const bool lookahead = !right_looking && !(getenv("CCGP_BIG_LOOKAHEAD") && !atoi(getenv("CCGP_BIG_LOOKAHEAD")));
+        // <= k-2, so it is launched as soon as column k-2 is final and overlaps the short serial kernels of column k-1
+        // (last-panel update, 64x64 factor + inverse on nb CTAs, solve).  Those run on a HIGH-PRIORITY internal stream so that
+        // their few CTAs take the first slots the bulk update's CTAs free (the bulk kernel alone fills every SM's shared
+        // memory); the bulk stays on the caller's stream.
+        // Measured (tools/bench_large_n.py): n = 2048 x 64 candidates 12.9 -> 12.4 ms, n = 1024 x 128 4.7 -> 5.2 ms (the extra
+        // launches cost more than the short chain they hide): on from 24 block columns, CCGP_BIG_LOOKAHEAD = 0 / 1 forces it.
+        const char* la_env = getenv("CCGP_BIG_LOOKAHEAD");
+        const bool lookahead = !right_looking && ((la_env && *la_env) ? atoi(la_env) != 0 : T >= 24);
         if (lookahead && !ws.side) {
-            BIGCK(cudaStreamCreateWithFlags(&ws.side, cudaStreamNonBlocking));
+            int lo = 0, hi = 0;
+            BIGCK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            BIGCK(cudaStreamCreateWithPriority(&ws.side, cudaStreamNonBlocking, hi));
             BIGCK(cudaEventCreateWithFlags(&ws.ev_main, cudaEventDisableTiming));
             BIGCK(cudaEventCreateWithFlags(&ws.ev_side[0], cudaEventDisableTiming));
             BIGCK(cudaEventCreateWithFlags(&ws.ev_side[1], cudaEventDisableTiming));
+        }
+        cudaStream_t crit = lookahead ? ws.side : stream;       // the serial chain of every block column
+        if (lookahead) {                                        // the chain starts after the build
+            BIGCK(cudaEventRecord(ws.ev_side[0], stream));
+            BIGCK(cudaStreamWaitEvent(crit, ws.ev_side[0], 0));
         }
         for (int k = 0; k < T; ++k) {
             if (!right_looking && k > 0) {
                 const int nrt = (nrp - k * 64 + 127) / 128;
                 const bool split = lookahead && k >= 2;
-                if (split) BIGCK(cudaStreamWaitEvent(stream, ws.ev_side[k & 1], 0));   // panels 0..k-2 are in (side stream)
-                big_update_kernel<false><<<dim3(nrt, nb), 256, 2 * BU_STAGE * 8, stream>>>(G, k, split ? 2 * (k - 1) : 0, 2 * k);
+                if (split) BIGCK(cudaStreamWaitEvent(crit, ws.ev_side[k & 1], 0));     // panels 0..k-2 are in (caller's stream)
+                big_update_kernel<false><<<dim3(nrt, nb), 256, 2 * BU_STAGE * 8, crit>>>(G, k, split ? 2 * (k - 1) : 0, 2 * k);
                 *launches += 1;
             }
-            big_potrf_kernel<<<nb, 256, 0, stream>>>(G, k);
+            big_potrf_kernel<<<nb, 256, 0, crit>>>(G, k);
             const int rt = (nrp - (k + 1) * 64) / 64;           // row tiles below the diagonal block
-            if (rt > 0 && right_looking) big_trsm_kernel<<<dim3(rt, nb), 64, 2 * 64 * 65 * 8, stream>>>(G, k);
-            else if (rt > 0) big_update_kernel<true><<<dim3((rt * 64 + 127) / 128, nb), 256, 2 * BU_STAGE * 8, stream>>>(G, k, 0, 2);
+            if (rt > 0 && right_looking) big_trsm_kernel<<<dim3(rt, nb), 64, 2 * 64 * 65 * 8, crit>>>(G, k);
+            else if (rt > 0) big_update_kernel<true><<<dim3((rt * 64 + 127) / 128, nb), 256, 2 * BU_STAGE * 8, crit>>>(G, k, 0, 2);
             *launches += 2;
-            if (lookahead && k + 2 < T) {                       // column k is final: panels 0..k of column k+2, on the side
-                BIGCK(cudaEventRecord(ws.ev_main, stream));
-                BIGCK(cudaStreamWaitEvent(ws.side, ws.ev_main, 0));
+            if (lookahead && k + 2 < T) {                       // column k is final: panels 0..k of column k+2, the bulk
+                BIGCK(cudaEventRecord(ws.ev_main, crit));
+                BIGCK(cudaStreamWaitEvent(stream, ws.ev_main, 0));
                 const int nrt2 = (nrp - (k + 2) * 64 + 127) / 128;
-                big_update_kernel<false><<<dim3(nrt2, nb), 256, 2 * BU_STAGE * 8, ws.side>>>(G, k + 2, 0, 2 * (k + 1));
-                BIGCK(cudaEventRecord(ws.ev_side[k & 1], ws.side));             // (k + 2) & 1: waited on at step k + 2, re-recorded after that wait
+                big_update_kernel<false><<<dim3(nrt2, nb), 256, 2 * BU_STAGE * 8, stream>>>(G, k + 2, 0, 2 * (k + 1));
+                BIGCK(cudaEventRecord(ws.ev_side[k & 1], stream));              // (k + 2) & 1: waited on at step k + 2, re-recorded after that wait
                 *launches += 1;
             }
             const int ct = T - (k + 1);                         // real block columns still to update
@@ -475,6 +487,10 @@ inline int bigchol_nll_batch(BigCholWorkspace& ws, cudaStream_t stream, int num_
                 big_syrk_kernel<<<dim3(ntiles, nb), 128, 2 * 64 * 72 * 8, stream>>>(G, k, rt);
                 *launches += 1;
             }
+        }
+        if (lookahead) {                                        // back on the caller's stream
+            BIGCK(cudaEventRecord(ws.ev_main, crit));
+            BIGCK(cudaStreamWaitEvent(stream, ws.ev_main, 0));
         }
         if (d_idx) big_logdet_out_kernel<<<(nb + 127) / 128, 128, 0, stream>>>(G, nb, d_nll, d_status);
         else big_finish_kernel<<<nb, 256, 0, stream>>>(G, b0, sigma2, mean_mode, tau, d_nll, d_beta, d_status);

@@ -13,7 +13,7 @@ struct BigCholWorkspace {
     double* linv = nullptr;    // chunk * 64 * 64: inverse of the current diagonal block, transposed (k-major B operand)
     size_t bytesA = 0;
     int cap = 0;
-    cudaStream_t side = nullptr;          // lookahead: the bulk of the NEXT block column's update runs here (bigchol.cuh)
+    cudaStream_t side = nullptr;          // lookahead: high-priority stream of the serial per-column chain (bigchol.cuh)
     cudaEvent_t ev_main = nullptr, ev_side[2] = {nullptr, nullptr};   // ev_side[k & 1]: the early part of column k is in
     void release() {
         if (A) cudaFree(A);
