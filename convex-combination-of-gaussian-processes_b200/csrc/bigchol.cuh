@@ -8,7 +8,8 @@
 //   update<false> : C(rows >= 64k, k) -= sum_{j<k} L(rows, j) L(k, j)'  for all 128-row tiles at once, the whole
 //                   K = 64k contraction accumulated in registers on the FP64 tensor path
 //                   (mma.sync.m8n8k4.f64 -> DMMA; tcgen05 has no FP64 kind), operands staged with cp.async
-//   potrf         : the 64x64 diagonal block in shared memory (one CTA per candidate) + its inverse
+//   potrf         : the 64x64 diagonal block in shared memory (one CTA per candidate) + its inverse, as 8x8 tiles on the
+//                   same tensor path (big_potrf_mma_kernel)
 //   update<true>  : rows below = C * inv(L_kk)' on the same tensor path (K = 64) instead of a 64-step substitution
 // plus build (mixed correlation tiles, 2 exp per entry, identity padding, rows y', 1') and finish (z-dots, beta,
 // Q_R, log det -> NLL, or the log-determinant alone for index subsets of a point pool).
@@ -19,7 +20,7 @@
 #pragma once
 #include <algorithm>
 #include <stdlib.h>
-#include "factor_engine.cuh"
+#include "factor_mma.cuh"
 #include "bigchol_ws.h"
 
 namespace ccgp {
@@ -163,6 +164,90 @@ __global__ void __launch_bounds__(256) big_potrf_kernel(BigArgs G, int k) {
         }
 #pragma unroll
         for (int r = 0; r < 64; ++r) out[(size_t)j * 64 + r] = x[r];            // linv[q = j][c = r] = inv(L)(r, j)
+    }
+}
+
+// The same step on the FP64 tensor path (the default; the kernel above remains for A/B runs, CCGP_BIG_POTRF_OLD=1).
+// The 64x64 block is 8x8 tiles of 8x8 in the fragment layout of factor_mma.cuh; 8 warps run the left-looking tile
+// algorithm of the small-n kernels over the 8 tile columns, and the inverse comes out of the SAME column steps:
+// X = inv(L)' solves X L' = I, so its tiles are "rows below" whose right-hand side is the identity,
+//   X(i, c) = (delta_ic I - sum_{J=i}^{c-1} X(i, J) L(c, J)') inv(L_cc)',  i <= c   (upper block-triangular).
+// Step c: warp c accumulates and factors the diagonal tile (mma_diag_impl: 8x8 Cholesky + inverse, every lane holding the
+// whole tile), warps w > c own L(w, c), warps w < c own X(w, c): seven products with inv(L_cc)' after one barrier.
+// 78 us -> ~9 us per block column at 64 candidates (the column-at-a-time panel loop and the 64-step substitution per
+// thread of the first version were the serial part of the large-n path: 2.5 of 12.4 ms at n = 2048).
+__global__ void __launch_bounds__(256) big_potrf_mma_kernel(BigArgs G, int k) {
+    __shared__ __align__(16) double Lt[36 * 64];     // tile (r, c), r >= c, at (r (r + 1) / 2 + c) * 64
+    __shared__ __align__(16) double Xt[36 * 64];     // tile X(i, c), i <= c, at (c (c + 1) / 2 + i) * 64
+    __shared__ __align__(16) double linv_t[64];      // inv(L_cc), row-major
+    __shared__ double s_ld[8];
+    __shared__ int s_badw[8];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    double* Ab = G.A + (size_t)b * G.stride + (size_t)(k * 64) * G.nrp + k * 64;
+    for (int e = tid; e < 4096; e += 256) {
+        const int r = e & 63, c = e >> 6, tr = r >> 3, tc = c >> 3;
+        if (tr >= tc) Lt[(tr * (tr + 1) / 2 + tc) * 64 + (r & 7) * 8 + (c & 7)] = Ab[(size_t)c * G.nrp + r];
+    }
+    __syncthreads();
+    FactorArgs FA;                                   // mma_diag_impl reads lay.n (all eight columns live) and tail0 only
+    FA.lay.n = 64; FA.tail0 = 0;
+    FactorResult res;
+    res.mant_all = 1.0; res.mant_tail = 1.0; res.es_all = 0; res.es_tail = 0; res.bad = 0;
+    for (int c = 0; c < 8; ++c) {
+        double2 acc = make_double2(0.0, 0.0), alt = make_double2(0.0, 0.0);
+        const double* ap;                            // this warp's operand tiles of panel J: ap + J * astep
+        int J0, astep;
+        if (w >= c) {
+            acc = ld2(Lt + (w * (w + 1) / 2 + c) * 64 + 2 * lane);
+            ap = Lt + (w * (w + 1) / 2) * 64 + 2 * lane; astep = 64; J0 = 0;                  // L(w, J)
+        } else {
+            ap = Xt + 2 * lane + w * 64; astep = 0; J0 = w;                                     // X(w, J) at (J (J + 1) / 2 + w) * 64
+        }
+        const double* bp = Lt + (c * (c + 1) / 2) * 64 + 2 * lane;                            // L(c, J)
+        for (int J = J0; J < c; ++J) {
+            const double2 a = (w >= c) ? ld2(ap + J * astep) : ld2(ap + (J * (J + 1) / 2) * 64);
+            const double2 bt = ld2(bp + J * 64);
+            mma884(acc.x, acc.y, a.x, negd(bt.x));
+            mma884(alt.x, alt.y, a.y, negd(bt.y));
+        }
+        acc.x += alt.x; acc.y += alt.y;
+        if (w == c) {
+            double* blk = Lt + (c * (c + 1) / 2 + c) * 64;
+            st2(blk + 2 * lane, acc.x, acc.y);
+            __syncwarp();
+            mma_diag_impl<true>(FA, blk, linv_t, c, lane, res, true);
+        }
+        __syncthreads();
+        if (w != c) {
+            const double2 li = ld2(linv_t + 2 * lane);
+            double2 x = make_double2(0.0, 0.0);
+            mma884(x.x, x.y, acc.x, li.x);
+            mma884(x.x, x.y, acc.y, li.y);
+            double* dst = (w > c) ? Lt + (w * (w + 1) / 2 + c) * 64 : Xt + (c * (c + 1) / 2 + w) * 64;
+            st2(dst + 2 * lane, x.x, x.y);
+        } else {                                     // X(c, c) = inv(L_cc)'
+            const int row = lane >> 2, col = 2 * (lane & 3);
+            st2(Xt + (c * (c + 1) / 2 + c) * 64 + 2 * lane, linv_t[col * 8 + row], linv_t[(col + 1) * 8 + row]);
+        }
+        __syncthreads();
+    }
+    if (lane == 0) { s_ld[w] = log(res.mant_all) + res.es_all * LN2; s_badw[w] = res.bad; }      // warp w factored tile column w
+    for (int e = tid; e < 4096; e += 256) {
+        const int r = e & 63, c = e >> 6, tr = r >> 3, tc = c >> 3;
+        if (r >= c) Ab[(size_t)c * G.nrp + r] = Lt[(tr * (tr + 1) / 2 + tc) * 64 + (r & 7) * 8 + (c & 7)];
+    }
+    double* out = G.linv + (size_t)b * 4096;         // out[q * 64 + cc] = inv(L)(cc, q) = X(q, cc)
+    for (int e = tid; e < 4096; e += 256) {
+        const int cc = e & 63, q = e >> 6, ti = q >> 3, tc = cc >> 3;
+        out[e] = (ti <= tc) ? Xt[(tc * (tc + 1) / 2 + ti) * 64 + (q & 7) * 8 + (cc & 7)] : 0.0;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double ld = 0.0;
+        int bad = 0;
+        for (int c = 0; c < 8; ++c) { ld += s_ld[c]; bad |= s_badw[c]; }
+        G.logdet[b] += ld;
+        if (bad) G.bad[b] = 1;
     }
 }
 
@@ -444,6 +529,7 @@ inline int bigchol_nll_batch(BigCholWorkspace& ws, cudaStream_t stream, int num_
         // memory); the bulk stays on the caller's stream.
         // Measured (tools/bench_large_n.py): n = 2048 x 64 candidates 12.9 -> 12.4 ms, n = 1024 x 128 4.7 -> 5.2 ms (the extra
         // launches cost more than the short chain they hide): on from 24 block columns, CCGP_BIG_LOOKAHEAD = 0 / 1 forces it.
+        const bool potrf_old = getenv("CCGP_BIG_POTRF_OLD") && atoi(getenv("CCGP_BIG_POTRF_OLD"));
         const char* la_env = getenv("CCGP_BIG_LOOKAHEAD");
         const bool lookahead = !right_looking && ((la_env && *la_env) ? atoi(la_env) != 0 : T >= 24);
         if (lookahead && !ws.side) {
@@ -467,7 +553,8 @@ inline int bigchol_nll_batch(BigCholWorkspace& ws, cudaStream_t stream, int num_
                 big_update_kernel<false><<<dim3(nrt, nb), 256, 2 * BU_STAGE * 8, crit>>>(G, k, split ? 2 * (k - 1) : 0, 2 * k);
                 *launches += 1;
             }
-            big_potrf_kernel<<<nb, 256, 0, crit>>>(G, k);
+            if (potrf_old) big_potrf_kernel<<<nb, 256, 0, crit>>>(G, k);
+            else big_potrf_mma_kernel<<<nb, 256, 0, crit>>>(G, k);
             const int rt = (nrp - (k + 1) * 64) / 64;           // row tiles below the diagonal block
             if (rt > 0 && right_looking) big_trsm_kernel<<<dim3(rt, nb), 64, 2 * 64 * 65 * 8, crit>>>(G, k);
             else if (rt > 0) big_update_kernel<true><<<dim3((rt * 64 + 127) / 128, nb), 256, 2 * BU_STAGE * 8, crit>>>(G, k, 0, 2);

@@ -168,6 +168,7 @@ struct FactorArgs {
     int team_map;         // team kernel: warp -> (team, role) mapping, see factor_team.cuh (CCGP_TEAM_MAP)
     int pack_slots;       // packed-residency kernel (factor_pack.cuh): tile slots per candidate, and the slot table
     uint32_t pack_off[256];   // off[J * 16 + r] = element offset of tile (r, J) in the candidate's slots
+    uint32_t pack_raw[256];   // producer/consumer kernel (factor_pc.cuh): element offset of the RAW tile (r, c)
     double* out0;         // NLL: nll          DET: log det (all pivots)
     double* out1;         // NLL: beta         DET: log det (tail pivots)
     double* out2;         // DET: -det(tail) (negated determinant, the ME criterion value)

@@ -99,9 +99,13 @@ int launch_factor_mma(ccgp_ctx* ctx, FactorArgs& A, int* launched) {
     const Layout& l = A.lay;
     if (A.family >= FAM_MATERN1D || env_int("CCGP_NO_MMA", 0)) return 0;
     const int NR = l.npad / 8;
-    const int kern = env_int("CCGP_KERNEL", 0);      // 0 auto, 1 warp, 3 team, 4 cta, 5 packed (factor_pack.cuh, opt-in)
+    const int kern = env_int("CCGP_KERNEL", 0);      // 0 auto, 1 warp, 3 team, 4 cta, 5 packed (factor_pack.cuh), 6 producer/consumer packed (factor_pc.cuh)
     if (kern == 5) {
         RC(launch_factor_pack(ctx, A, launched));
+        if (*launched) return 0;
+    }
+    if (kern == 6) {
+        RC(launch_factor_pc(ctx, A, launched));
         if (*launched) return 0;
     }
     if ((kern == 0 && NR <= 10) || kern == 1) {

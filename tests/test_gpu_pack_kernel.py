@@ -65,3 +65,40 @@ def test_packed_kernel_soak_vs_shipped_choice(engine, n, d, logs):
             first = nll
     finally:
         os.environ.pop("CCGP_KERNEL", None)
+
+
+@pytest.mark.parametrize("n,d,logs,B", [(100, 2, 1, (1 << 15) + 37), (104, 2, 0, 4099), (96, 2, 0, 5), (50, 9, 0, 1 << 14), (21, 2, 0, 2000)])
+def test_producer_consumer_kernel_bit_identical_to_packed(engine, n, d, logs, B):
+    """csrc/factor_pc.cuh (CCGP_KERNEL=6): the packed kernel with the column assembly moved to producer warps (setmaxnreg,
+    named barriers, a slot plan with separate raw and solved slots).  Same arithmetic tile by tile, so the values must
+    be bit-identical to the packed kernel's, for batch sizes that leave consumers without work in the last CTA too."""
+    rng = np.random.default_rng(7 * n + d)
+    if (n, d) == (100, 2):
+        X, y, s2 = workloads.m1_design()
+    else:
+        X = rng.uniform(-1, 1, (n, d)); y = rng.normal(size=n); s2 = 1.0
+    engine.set_design(X, y)
+    if logs:
+        th, scale = workloads.m1_candidates(B), LOGSCALE
+    else:
+        t0 = 8.0 / d * n ** (1.0 / d)
+        th = np.column_stack([rng.uniform(0.2, 0.8, B)] + [rng.uniform(0.5 * t0, 1.5 * t0, B) for _ in range(d)] + [rng.uniform(0.5, 3.0, B)])
+        scale = 0
+    old = os.environ.get("CCGP_KERNEL")
+    try:
+        os.environ["CCGP_KERNEL"] = "5"
+        ref, rbeta, rst = engine.nll_batch(th, GAUSS_ANISO_LAMBDA, s2, scale=scale)
+        assert 500 <= engine.last_nll_config()["variant"] < 600
+        for split in ("0", "1", "2"):
+            os.environ["CCGP_KERNEL"] = "6"
+            os.environ["CCGP_PC_SPLIT"] = split
+            nll, beta, st = engine.nll_batch(th, GAUSS_ANISO_LAMBDA, s2, scale=scale)
+            assert engine.last_nll_config()["variant"] >= 600
+            assert np.array_equal(st, rst)
+            assert np.array_equal(nll, ref, equal_nan=True) and np.array_equal(beta, rbeta, equal_nan=True)
+    finally:
+        os.environ.pop("CCGP_PC_SPLIT", None)
+        if old is None:
+            os.environ.pop("CCGP_KERNEL", None)
+        else:
+            os.environ["CCGP_KERNEL"] = old

@@ -28,14 +28,17 @@ cand = torch.from_numpy(np.asfortranarray(nat).T.copy()).to(dev)
 out = eng.nll_batch_dev(cand, GAUSS_ANISO_LAMBDA, 1.0)
 torch.cuda.synchronize()
 l0 = eng.launch_count
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record(stream)
-reps = 3
+reps = 5
+tms = []
 for _ in range(reps):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
     eng.nll_batch_dev(cand, GAUSS_ANISO_LAMBDA, 1.0, out_nll=out[0], out_beta=out[1], out_status=out[2])
-e1.record(stream)
-torch.cuda.synchronize()
-ms = e0.elapsed_time(e1) / reps
+    e1.record(stream)
+    torch.cuda.synchronize()
+    tms.append(e0.elapsed_time(e1))
+ms = sorted(tms)[len(tms) // 2]
+print("per-rep ms:", " ".join("%.2f" % t for t in tms))
 flop = n ** 3 / 3 + n ** 2 / 2 + 2 * n * n + (n * (n - 1) / 2) * 11
 print("n=%d B=%d: %.2f ms per batch, %.1f evals/s, %.2f TFLOP/s FP64 (algorithmic), %d launches/batch, bad=%d" % (
     n, B, ms, B / (ms * 1e-3), flop * B / (ms * 1e-3) / 1e12, (eng.launch_count - l0) // reps, int((out[2] != 0).sum())))
