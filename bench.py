@@ -329,6 +329,7 @@ def run_ours(args, rank, world, local_rank):
     # ---- M2: ME subset (Schur) determinants/sec, pool(1000) x params(1000) per step, resident inputs
     me = None
     pred = None
+    large_n = None
     if not args.no_me:
         eng.set_stream(stream.cuda_stream)
         D_old, pool = workloads.me_pool()
@@ -435,6 +436,51 @@ def run_ours(args, rank, world, local_rank):
                              "note": "frac: SURVEY 8(d) count of the reference's explicit-inverse algorithm (2 n^2 per site); "
                                      "frac_executed: the forward-solve algorithm the kernel runs (n^2 per site); 2 n exp per site in neither"},
                 "finite": bool(torch.isfinite(pm).all().item())}
+        # ---- large-n blocked FP64-tensor path (north_star: synthetic n = 2048, 2-D anisotropic; SURVEY 8d ME-B(1)), rank 0
+        if rank == 0:
+            n_big, B_big = 2048, 64
+            Xb = workloads.synthetic_pool(n_big, seed=2048)
+            yb = np.sin(3 * Xb[:, 0]) * np.cos(2 * Xb[:, 1])
+            rng_b = np.random.default_rng(1)
+            h2 = 4.0 / n_big
+            nat_b = np.column_stack([rng_b.uniform(0.2, 0.8, B_big), rng_b.uniform(1.2, 2.5, B_big) / h2,
+                                     rng_b.uniform(1.2, 2.5, B_big) / h2, rng_b.uniform(0.5, 2, B_big)])
+            eng.set_design(Xb, yb)
+            d_cb = torch.from_numpy(np.asfortranarray(nat_b).T.copy()).to(dev)
+            ob = eng.nll_batch_dev(d_cb, GAUSS_ANISO_LAMBDA, 1.0)
+            eng.nll_batch_dev(d_cb, GAUSS_ANISO_LAMBDA, 1.0, out_nll=ob[0], out_beta=ob[1], out_status=ob[2])
+            torch.cuda.synchronize(dev)
+            l0 = eng.launch_count
+            evs = []
+            for _ in range(9):                                   # queued back to back; clocks sampled while they run
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                eng.nll_batch_dev(d_cb, GAUSS_ANISO_LAMBDA, 1.0, out_nll=ob[0], out_beta=ob[1], out_status=ob[2])
+                e1.record(stream)
+                evs.append((e0, e1))
+            big_clk, big_pw = [], []
+            try:
+                import pynvml
+                pynvml.nvmlInit()
+                hnd = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+                while not evs[-1][1].query():
+                    big_clk.append(pynvml.nvmlDeviceGetClockInfo(hnd, pynvml.NVML_CLOCK_SM))
+                    big_pw.append(pynvml.nvmlDeviceGetPowerUsage(hnd) / 1000.0)
+                    time.sleep(0.01)
+            except Exception:
+                pass
+            torch.cuda.synchronize(dev)
+            tb = [a.elapsed_time(b) for a, b in evs]
+            b_ms = sorted(tb)[len(tb) // 2]
+            bflop = B_big * (n_big ** 3 / 3.0 + 2.5 * n_big * n_big)
+            large_n = {"metric": "large-n NLL evals/sec (blocked FP64 tensor path)", "value": B_big / (b_ms * 1e-3), "unit": "evals/s",
+                       "workload": "synthetic n=2048 d=2 anisotropic, 64 candidates per batch, matrices in HBM (2.2 GB)",
+                       "ms_per_batch": b_ms, "ms_per_batch_all": [round(t, 3) for t in tb], "launches_per_batch": int((eng.launch_count - l0) // 9),
+                       "sm_mhz_during": (float(np.median(big_clk)) if big_clk else None), "power_w_max_during": (max(big_pw) if big_pw else None),
+                       "roofline": {"bound": "tensor", "achieved": bflop / (b_ms * 1e-3) / 1e12, "peak": peak / 1e12, "unit": "TFLOP/s",
+                                    "frac": bflop / (b_ms * 1e-3) / peak, "flop_per_eval": bflop / B_big},
+                       "not_pd_candidates": int((ob[2] != 0).sum().item())}
+            eng.set_design(X, y)
         eng.set_stream(None)
 
     _log('ME/predict blocks done')
@@ -550,7 +596,7 @@ def run_ours(args, rank, world, local_rank):
                     "d2h_bytes_per_step": int(B * 20), "timed": "wall clock around %d synchronous ccgp_nll_batch host calls" % ksteps},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "me": me, "predict": pred, "strong": strong,
+            "me": me, "predict": pred, "large_n": large_n, "strong": strong,
         }
         if args.scaling == "strong" and strong:
             st = strong["m1_2^20_n100"]
