@@ -80,7 +80,7 @@ int get_tiletab(ccgp_ctx* ctx, const Layout& l, int TR, int TC, const uint32_t**
 // factor_launch.cu / factor_mma_launch.cu
 int launch_factor(ccgp_ctx* ctx, FactorArgs& A);
 int launch_factor_mma(ccgp_ctx* ctx, FactorArgs& A, int* launched);
-int launch_factor_pack(ccgp_ctx* ctx, FactorArgs& A, int* launched);   // factor_pack_launch.cu
+int launch_factor_pack(ccgp_ctx* ctx, FactorArgs& A, int* launched, int min_warps = 1);   // factor_pack_launch.cu
 int launch_factor_pc(ccgp_ctx* ctx, FactorArgs& A, int* launched);     // factor_pc_launch.cu
 // multi.cu -- the front context fans every batch out over its per-GPU contexts
 void ccgp_set_create_error(const char* msg);

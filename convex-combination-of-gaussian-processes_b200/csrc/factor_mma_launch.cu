@@ -92,6 +92,7 @@ static int launch_factor_warp(ccgp_ctx* ctx, FactorArgs& A, int* launched) {
 // returns 1 when the candidate batch was launched on a DMMA kernel, 0 when none applies.
 // Choice by tile rows NR = npad/8, measured on B200 (profiles/r01_tune_kernels.txt):
 //   NR <= 10 (n <= ~78): one warp per candidate -- shared memory lets 2-3 candidates share a sub-partition
+//   NR 11..13 and d = 2: the packed-residency kernel (factor_pack.cuh), eight one-warp candidates per SM
 //   NR <= 14 (n <= ~110): three warps per candidate on one sub-partition (shared memory caps residency at 4/SM)
 //   larger: the CTA-per-candidate DMMA kernel (factor_mma.cuh), then the DFMA kernel / HBM path
 int launch_factor_mma(ccgp_ctx* ctx, FactorArgs& A, int* launched) {
@@ -110,6 +111,13 @@ int launch_factor_mma(ccgp_ctx* ctx, FactorArgs& A, int* launched) {
     }
     if ((kern == 0 && NR <= 10) || kern == 1) {
         RC(launch_factor_warp(ctx, A, launched));
+        if (*launched) return 0;
+    }
+    // 2-D designs of 11..13 tile rows (n = 79..102): eight packed candidates per SM fit and beat four teams by 4-6 %
+    // (profiles/r02_pack_vs_team.txt: n = 84/88/96/100 -> +6/+5/+4/+4 %; with d >= 3 the packed kernel's generic
+    // distance loop loses 12 %, and from n = 103 only four candidates fit)
+    if (kern == 0 && A.d == 2 && NR >= 11 && NR <= 13 && !env_int("CCGP_NO_PACK", 0)) {
+        RC(launch_factor_pack(ctx, A, launched, 8));
         if (*launched) return 0;
     }
     if ((kern == 0 && NR <= 14) || kern == 3) {

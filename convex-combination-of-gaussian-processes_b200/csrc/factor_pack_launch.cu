@@ -8,7 +8,7 @@ struct PackVariant { int maxt, maxw; factor_fn fn_d0, fn_d2; };
 static const PackVariant g_pack_variants[] = {PV(14, 8)};
 #undef PV
 
-int launch_factor_pack(ccgp_ctx* ctx, FactorArgs& A, int* launched) {
+int launch_factor_pack(ccgp_ctx* ctx, FactorArgs& A, int* launched, int min_warps) {
     *launched = 0;
     const Layout& l = A.lay;
     const int NR = l.npad / 8;
@@ -25,7 +25,7 @@ int launch_factor_pack(ccgp_ctx* ctx, FactorArgs& A, int* launched) {
         const int w = std::min(std::min(fit, v.maxw), want > 0 ? want : 64);
         if (w > nw) { nw = w; var = &v; }
     }
-    if (!var || nw < 1) return 0;
+    if (!var || nw < 1 || nw < min_warps) return 0;
     if (env_int("CCGP_PACK_EVEN", 1) && nw > 4) nw = nw / 4 * 4;     // the same number of candidates on every sub-partition
     const size_t smem = csm + wsm * nw;
     factor_fn fn = (A.d == 2) ? var->fn_d2 : var->fn_d0;

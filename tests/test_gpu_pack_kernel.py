@@ -1,5 +1,5 @@
-"""GPU (-m gpu): the opt-in packed-residency NLL kernel (csrc/factor_pack.cuh, CCGP_KERNEL=5) against the oracle's golden
-values and against the shipped kernel choice on large seeded batches (the soak that caught wrong values in experimental
+"""GPU (-m gpu): the packed-residency NLL kernel (csrc/factor_pack.cuh; default for 2-D designs of 79..102 points, CCGP_KERNEL=5 elsewhere) against the oracle's golden
+values and against the team / warp kernels on large seeded batches (the soak that caught wrong values in experimental
 builds of this kernel: a few percent of the candidates off by 1e-2, different from run to run)."""
 import os
 
@@ -49,7 +49,11 @@ def test_packed_kernel_soak_vs_shipped_choice(engine, n, d, logs):
         th = np.column_stack([rng.uniform(0.2, 0.8, B)] + [rng.uniform(0.5 * t0, 1.5 * t0, B) for _ in range(d)] + [rng.uniform(0.5, 3.0, B)])
         scale = 0
     os.environ.pop("CCGP_KERNEL", None)
-    ref, rbeta, rst = engine.nll_batch(th, GAUSS_ANISO_LAMBDA, s2, scale=scale)
+    os.environ["CCGP_NO_PACK"] = "1"                                 # the team / warp kernels (the packed one is the default for d = 2, n = 79..102)
+    try:
+        ref, rbeta, rst = engine.nll_batch(th, GAUSS_ANISO_LAMBDA, s2, scale=scale)
+    finally:
+        os.environ.pop("CCGP_NO_PACK", None)
     assert engine.last_nll_config()["variant"] < 500
     os.environ["CCGP_KERNEL"] = "5"
     try:

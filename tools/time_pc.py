@@ -17,7 +17,8 @@ eng = ccgp_b200.Engine(0)
 stream = torch.cuda.current_stream(dev)
 eng.set_stream(stream.cuda_stream)
 KEYS = ("CCGP_KERNEL", "CCGP_PACK_WARPS", "CCGP_PACK_EVEN", "CCGP_TEAM_NW", "CCGP_DUO_CANDS", "CCGP_TEAM_MAP")
-sizes = [int(a) for a in sys.argv[1:]] or [100]
+sizes = [int(a.split(":")[0]) for a in sys.argv[1:]] or [100]
+dims = {int(a.split(":")[0]): int(a.split(":")[1]) for a in sys.argv[1:] if ":" in a}       # "n:d" overrides the dimension
 rng = np.random.default_rng(5)
 for n in sizes:
     if n == 100:
@@ -27,7 +28,7 @@ for n in sizes:
         cand = workloads.m1_candidates(B)
         scale = LOGSCALE
     else:
-        d = {14: 2, 50: 9, 64: 4, 90: 9}.get(n, 2)
+        d = dims.get(n, {14: 2, 50: 9, 64: 4, 90: 9}.get(n, 2))
         fam = GAUSS_ISO if d > 2 else GAUSS_ANISO_LAMBDA
         X = rng.uniform(-1, 1, (n, d)); y = rng.normal(size=n); s2 = 1.0
         B = int(min(1 << 20, max(1 << 16, (1 << 31) // (n * n * n // 3 + 1))))
@@ -40,7 +41,7 @@ for n in sizes:
     nll = torch.empty(B, dtype=torch.float64, device=dev)
     beta = torch.empty(B, dtype=torch.float64, device=dev)
     status = torch.empty(B, dtype=torch.int32, device=dev)
-    configs = [("pack w8", {"CCGP_KERNEL": "5"}), ("auto", {}), ("prod/cons", {"CCGP_KERNEL": "6"})]
+    configs = [("pack w8", {"CCGP_KERNEL": "5"}), ("auto", {})] + ([("prod/cons", {"CCGP_KERNEL": "6"})] if os.environ.get("TIME_PC", "1") == "1" else [])
     ref = None
     for name, env in configs:
         for kk in KEYS:
