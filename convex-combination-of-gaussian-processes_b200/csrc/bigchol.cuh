@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(256) big_potrf_kernel(BigArgs G, int k) {
 //   X(i, c) = (delta_ic I - sum_{J=i}^{c-1} X(i, J) L(c, J)') inv(L_cc)',  i <= c   (upper block-triangular).
 // Step c: warp c accumulates and factors the diagonal tile (mma_diag_impl: 8x8 Cholesky + inverse, every lane holding the
 // whole tile), warps w > c own L(w, c), warps w < c own X(w, c): seven products with inv(L_cc)' after one barrier.
-// 78 us -> ~9 us per block column at 64 candidates (the column-at-a-time panel loop and the 64-step substitution per
+// 78 us -> 22 us per block column (ncu, 128 candidates) (the column-at-a-time panel loop and the 64-step substitution per
 // thread of the first version were the serial part of the large-n path: 2.5 of 12.4 ms at n = 2048).
 __global__ void __launch_bounds__(256) big_potrf_mma_kernel(BigArgs G, int k) {
     __shared__ __align__(16) double Lt[36 * 64];     // tile (r, c), r >= c, at (r (r + 1) / 2 + c) * 64

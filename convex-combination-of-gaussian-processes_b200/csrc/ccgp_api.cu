@@ -13,6 +13,7 @@
 #include "ccgp_ctx.h"
 #include "predict_kernel.cuh"
 #include "predict_mma.cuh"
+#include "rinv_mma.cuh"
 #include "me_kernel.cuh"
 #include "bigchol.cuh"
 
@@ -574,13 +575,38 @@ static int rinv_common(ccgp_ctx* ctx, int family, int scale, const double* cand,
     A.cand = d_cand; A.ldc = B; A.n_params = B; A.family = family; A.logscale = scale; A.sigma2 = 1.0; A.W = B;
     A.out_mode = OUT_NLL;
     P.out_rinv = out_Rinv ? d_rinv : nullptr; P.out_beta = d_beta; P.out_rcond = out_rcond ? d_rcond : nullptr; P.status = d_status;
-    RC(get_tiletab(ctx, l, 4, 4, &A.tiletab));
-    auto fn = rinv_kernel<TEAM, 4, 4, 2>;
-    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int64_t grid = std::min<int64_t>(B, (int64_t)ctx->num_sm * 2);
-    fn<<<(unsigned)grid, TEAM, smem, ctx->stream>>>(P);
-    CK(cudaGetLastError());
-    ctx->launches++;
+    // Gaussian families: the tensor-path kernel (rinv_mma.cuh) while factor + V tiles fit shared memory
+    bool launched = false;
+    if (family < CCGP_MATERN1D && !env_int("CCGP_RINV_OLD", 0)) {
+        const int NR = l.npad / 8;
+        const size_t smem2 = rinv_mma_smem_bytes(l, A.d);
+        typedef void (*rfn)(const RinvArgs);
+        rfn fn2 = nullptr;
+        if (NR <= 7) fn2 = (A.d == 2) ? rinv_mma_kernel<2, 2> : rinv_mma_kernel<2, 0>;
+        else if (NR <= 13) fn2 = (A.d == 2) ? rinv_mma_kernel<4, 2> : rinv_mma_kernel<4, 0>;
+        else if (NR <= 16) fn2 = (A.d == 2) ? rinv_mma_kernel<5, 2> : rinv_mma_kernel<5, 0>;
+        if (fn2 && smem2 <= (size_t)ctx->max_smem_optin) {
+            CK(cudaFuncSetAttribute(fn2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            int nb = 0;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn2, RM_NW * 32, smem2));
+            if (nb >= 1) {
+                const int64_t grid2 = std::min<int64_t>(B, (int64_t)nb * ctx->num_sm);
+                fn2<<<(unsigned)grid2, RM_NW * 32, smem2, ctx->stream>>>(P);
+                CK(cudaGetLastError());
+                ctx->launches++;
+                launched = true;
+            }
+        }
+    }
+    if (!launched) {
+        RC(get_tiletab(ctx, l, 4, 4, &A.tiletab));
+        auto fn = rinv_kernel<TEAM, 4, 4, 2>;
+        CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int64_t grid = std::min<int64_t>(B, (int64_t)ctx->num_sm * 2);
+        fn<<<(unsigned)grid, TEAM, smem, ctx->stream>>>(P);
+        CK(cudaGetLastError());
+        ctx->launches++;
+    }
     if (out_Rinv) CK(cudaMemcpyAsync(out_Rinv, d_rinv, (size_t)B * nn * 8, cudaMemcpyDeviceToHost, ctx->stream));
     if (out_beta) CK(cudaMemcpyAsync(out_beta, d_beta, (size_t)B * 8, cudaMemcpyDeviceToHost, ctx->stream));
     if (out_rcond) CK(cudaMemcpyAsync(out_rcond, d_rcond, (size_t)B * 8, cudaMemcpyDeviceToHost, ctx->stream));
