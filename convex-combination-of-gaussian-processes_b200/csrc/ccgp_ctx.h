@@ -25,6 +25,8 @@ struct ccgp_ctx {
     int n = 0, d = 0;
     double* d_X = nullptr;
     double* d_y = nullptr;
+    size_t cap_X = 0, cap_y = 0;          // bytes allocated behind d_X / d_y (set_design reuses them)
+    std::vector<double> h_X, h_y;         // host copy of the design in place: an identical set_design is a no-op
     double span2[MAXD] = {0};   // squared coordinate ranges of the shared design
     int twonu = 10;             // Matern smoothness of the 1-D families, 2*nu (reference default nu = 5)
     double mnorm = 1.0 / 384.0; // 1 / (Gamma(nu) 2^(nu-1))

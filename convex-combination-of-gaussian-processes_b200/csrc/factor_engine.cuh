@@ -201,10 +201,11 @@ __device__ __forceinline__ void prod_accum(double& mant, int& es, double piv) {
 }
 
 // `c`/`ld`: the candidate's parameter row (element k at c[k*ld]) -- global memory, or a staged copy
-__device__ inline void load_params_from(const FactorArgs& A, const double* c, const int64_t ld, Prm* prm) {
+// `family`: the component family of THIS row (the predictive kernels read a second row of another family, quirk Q2)
+__device__ inline void load_params_fam(const FactorArgs& A, const int family, const double* c, const int64_t ld, Prm* prm) {
     const int d = A.d;
     double p, rho;
-    if (A.family == FAM_ANISO) {
+    if (family == FAM_ANISO) {
         double lam;
         if (A.logscale) {
             for (int k = 0; k < d; ++k) prm->wts[k] = exp(c[k * ld]);
@@ -233,9 +234,9 @@ __device__ inline void load_params_from(const FactorArgs& A, const double* c, co
     double w = p * p + (1.0 - p) * (1.0 - p);
     prm->kind = 0;
     prm->w = w;
-    if (A.family >= FAM_MATERN1D) {
+    if (family >= FAM_MATERN1D) {
         const double sn = sqrt(2.0 * A.twonu);                  // 2 sqrt(nu) = sqrt(4 nu) = sqrt(2 * twonu)
-        prm->kind = (A.family == FAM_MATERN1D) ? 1 : 2;
+        prm->kind = (family == FAM_MATERN1D) ? 1 : 2;
         prm->c1 = sn / prm->wts[0];
         prm->c2 = (prm->kind == 1) ? sn / (rho * prm->wts[0]) : 1.0 / (rho * prm->wts[0]);
         prm->twonu = A.twonu;
@@ -250,6 +251,9 @@ __device__ inline void load_params_from(const FactorArgs& A, const double* c, co
     for (int k = 0; k < d; ++k) smax += prm->wts[k] * A.span2[k];
     smax *= fmax(rho, 1.0);
     prm->clamp = (A.force_clamp || !(smax < 1e6)) ? 1 : 0;   // 1e6: the table-driven exp's int32 range
+}
+__device__ inline void load_params_from(const FactorArgs& A, const double* c, const int64_t ld, Prm* prm) {
+    load_params_fam(A, A.family, c, ld, prm);
 }
 __device__ inline void load_params(const FactorArgs& A, int64_t pi, Prm* prm) {
     load_params_from(A, A.cand + pi, A.ldc, prm);

@@ -71,9 +71,7 @@ __global__ void __launch_bounds__(TEAM, MINB) predict_kernel(const PredictArgs P
         if (tid == 0) load_params(A, s, prm);
         if (tid == 32 % TEAM) {
             if (P.candv) {
-                FactorArgs B = A;
-                B.cand = P.candv; B.ldc = P.ldcv; B.family = P.vec_family;
-                load_params(B, s, prmv);
+                load_params_fam(A, P.vec_family, P.candv + s, P.ldcv, prmv);     // (no local copy of the 2 KB argument block)
             } else {
                 load_params(A, s, prmv);
             }

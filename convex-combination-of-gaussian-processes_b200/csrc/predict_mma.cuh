@@ -62,9 +62,7 @@ __global__ void __launch_bounds__(PM_NW * 32, 2) predict_mma_kernel(const Predic
         if (tid == 0) load_params(A, s, prm);
         if (tid == 32) {
             if (P.candv) {
-                FactorArgs V = A;
-                V.cand = P.candv; V.ldc = P.ldcv; V.family = P.vec_family;
-                load_params(V, s, prmv);
+                load_params_fam(A, P.vec_family, P.candv + s, P.ldcv, prmv);     // (no local copy of the 2 KB argument block)
             } else {
                 load_params(A, s, prmv);
             }
