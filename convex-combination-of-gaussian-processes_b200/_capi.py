@@ -18,6 +18,7 @@ SYMBOLS = [
     "ccgp_kmedoids_pam", "ccgp_me_schur_paired", "ccgp_me_schur_stencil", "ccgp_rcond_batch",
     "ccgp_create_multi", "ccgp_num_gpus", "ccgp_collective_count", "ccgp_measure_fp64_peak_dmma",
     "ccgp_cgp_objective_batch", "ccgp_cgp_jackknife",
+    "ccgp_factors_create", "ccgp_factors_predict", "ccgp_factors_predict_dev", "ccgp_factors_info", "ccgp_factors_destroy",
 ]
 
 _lib = None
@@ -68,6 +69,11 @@ def load():
     pred = [vp, i32, dp, i64, i64, i32, dp, i64, dp, i64, f64, dp, dp, ip]
     lib.ccgp_predict.argtypes = pred
     lib.ccgp_predict_dev.argtypes = pred
+    lib.ccgp_factors_create.argtypes = [vp, i32, dp, i64, i64, i32, dp, i64, C.POINTER(C.c_void_p)]
+    lib.ccgp_factors_predict.argtypes = [vp, vp, dp, i64, f64, dp, dp, ip]
+    lib.ccgp_factors_predict_dev.argtypes = [vp, vp, dp, i64, f64, dp, dp, ip]
+    lib.ccgp_factors_info.argtypes = [vp, vp, C.POINTER(C.c_int64), C.POINTER(C.c_int), C.POINTER(C.c_int64)]
+    lib.ccgp_factors_destroy.argtypes = [vp, vp]
     me = [vp, dp, i32, i32, dp, i32, i64, dp, i64, i64, dp, dp, ip]
     lib.ccgp_me_schur_batch.argtypes = me
     lib.ccgp_me_schur_batch_dev.argtypes = me

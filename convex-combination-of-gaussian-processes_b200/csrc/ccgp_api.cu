@@ -288,6 +288,7 @@ extern "C" int ccgp_set_design(ccgp_ctx* ctx, const double* X, int n, int d, con
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->n = 0;                                              // no design in place until the copies below are done
+    ctx->design_gen++;                                       // factors created on the previous design are refused from here on
     ctx->h_X.clear(); ctx->h_y.clear();
     if (bx > ctx->cap_X) {
         if (ctx->d_X) { CK(cudaFree(ctx->d_X)); ctx->d_X = nullptr; ctx->cap_X = 0; }
@@ -673,6 +674,39 @@ static int launch_predict(ccgp_ctx* ctx, PredictArgs& P) {
     return 0;
 }
 
+// The tensor-path predictive kernel (predict_mma.cuh) when its factor + site buffers fit shared memory; *launched = 0 otherwise.
+static int predict_mma_launch(ccgp_ctx* ctx, PredictArgs& P, int* launched) {
+    *launched = 0;
+    const FactorArgs& A = P.F;
+    const Layout& l = A.lay;
+    const int NR = l.npad / 8;
+    const size_t smem = predict_mma_smem_bytes(l, A.d);
+    typedef void (*pfn)(const PredictArgs);
+    pfn fn = nullptr;
+    if (NR <= 7) fn = (A.d == 2) ? predict_mma_kernel<2, 2> : predict_mma_kernel<2, 0>;
+    else if (NR <= 13) fn = (A.d == 2) ? predict_mma_kernel<4, 2> : predict_mma_kernel<4, 0>;
+    else if (NR <= 16) fn = (A.d == 2) ? predict_mma_kernel<5, 2> : predict_mma_kernel<5, 0>;
+    if (!fn || smem > (size_t)ctx->max_smem_optin) return 0;
+    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int nb = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, PM_NW * 32, smem));
+    if (nb < 1) return 0;
+    const int64_t slots = (int64_t)nb * ctx->num_sm;
+    P.t_chunks = 1;
+    if (P.fac_mode == 2 && A.W < slots) {
+        // stored factors, fewer rows than resident CTAs: the sites of a row are split over several CTAs (64 sites = one pass
+        // of the four warps is the smallest useful share)
+        const int64_t passes = (P.T + 63) / 64;
+        P.t_chunks = (int)std::max<int64_t>(1, std::min<int64_t>(passes, slots / A.W));
+    }
+    const int64_t grid = std::min<int64_t>(A.W * P.t_chunks, slots);
+    fn<<<(unsigned)grid, PM_NW * 32, smem, ctx->stream>>>(P);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    *launched = 1;
+    return 0;
+}
+
 extern "C" int ccgp_predict_dev(ccgp_ctx* ctx, int family, const double* d_pars, int64_t S, int64_t ldp,
                                 int vec_family, const double* d_pars_vec, int64_t ldpv, const double* d_Xnew,
                                 int64_t T, double sigma2, double* d_mean, double* d_var, int32_t* d_status) {
@@ -700,26 +734,9 @@ extern "C" int ccgp_predict_dev(ccgp_ctx* ctx, int family, const double* d_pars,
     const int n = ctx->n;
     // Gaussian families: the tensor-path kernel (predict_mma.cuh) while its factor + site buffers fit shared memory
     if (family < CCGP_MATERN1D && (d_pars_vec == nullptr || vec_family < CCGP_MATERN1D) && !env_int("CCGP_PREDICT_OLD", 0)) {
-        const Layout& l = A.lay;
-        const int NR = l.npad / 8;
-        const size_t smem = predict_mma_smem_bytes(l, A.d);
-        typedef void (*pfn)(const PredictArgs);
-        pfn fn = nullptr;
-        if (NR <= 7) fn = (A.d == 2) ? predict_mma_kernel<2, 2> : predict_mma_kernel<2, 0>;
-        else if (NR <= 13) fn = (A.d == 2) ? predict_mma_kernel<4, 2> : predict_mma_kernel<4, 0>;
-        else if (NR <= 16) fn = (A.d == 2) ? predict_mma_kernel<5, 2> : predict_mma_kernel<5, 0>;
-        if (fn && smem <= (size_t)ctx->max_smem_optin) {
-            CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            int nb = 0;
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, PM_NW * 32, smem));
-            if (nb >= 1) {
-                const int64_t grid = std::min<int64_t>(S, (int64_t)nb * ctx->num_sm);
-                fn<<<(unsigned)grid, PM_NW * 32, smem, ctx->stream>>>(P);
-                CK(cudaGetLastError());
-                ctx->launches++;
-                return CCGP_OK;
-            }
-        }
+        int launched = 0;
+        RC(predict_mma_launch(ctx, P, &launched));
+        if (launched) return CCGP_OK;
     }
     if (n <= 32) return launch_predict<64, 4, 4, 1, 8>(ctx, P);
     if (n <= 64) return launch_predict<128, 4, 4, 2, 4>(ctx, P);
@@ -786,6 +803,195 @@ extern "C" int ccgp_predict(ccgp_ctx* ctx, int family, const double* pars, int64
         return 0;
     };
     rc = pipeline();
+    cudaError_t e1 = cudaStreamSynchronize(ctx->copy_stream), e2 = cudaStreamSynchronize(ctx->stream);
+    if (rc) return rc;
+    CK(e1);
+    CK(e2);
+    return CCGP_OK;
+}
+
+// ------------------------------------------------------------------ factors kept on the device
+// `factors.frame` ([A]:572-592) computes R.Inv, beta and the factor vectors of every posterior row once and ships them
+// through a data.frame (n^2 + 2n + 5 doubles per row); `prediction` ([A]:637-654) then walks rows x sites.  Here the
+// per-row state is the Cholesky factor in the predictive kernel's own layout, written to HBM by ccgp_factors_create and
+// read back by ccgp_factors_predict, which runs only the site phase: same arithmetic as ccgp_predict on the same factor,
+// so the tables are bit-identical to a direct call.
+static int factors_predict_slice_dev(ccgp_ctx* ctx, const ccgp_factors* f, int64_t s0, int64_t ns, const double* d_Xnew,
+                                     int64_t T, double sigma2, double* d_mean, double* d_var, int32_t* d_status) {
+    if (!f->stored)
+        return ccgp_predict_dev(ctx, f->family, f->d_pars + s0, ns, f->S, f->vec_family, f->d_pv ? f->d_pv + s0 : nullptr, f->S,
+                                d_Xnew, T, sigma2, d_mean, d_var, d_status);
+    PredictArgs P;
+    memset(&P, 0, sizeof(P));
+    FactorArgs& A = P.F;
+    A.lay = make_layout(ctx->n, 2);
+    A.d = ctx->d; A.design_mode = DESIGN_SHARED; memcpy(A.span2, ctx->span2, sizeof(A.span2)); A.twonu = ctx->twonu; A.mnorm = ctx->mnorm; A.X = ctx->d_X; A.y = ctx->d_y; A.n_designs = 1;
+    A.cand = f->d_pars + s0; A.ldc = f->S; A.n_params = ns; A.family = f->family; A.logscale = 0; A.sigma2 = sigma2; A.W = ns;
+    A.out_mode = OUT_NLL;
+    P.Xnew = d_Xnew; P.T = T; P.candv = f->d_pv ? f->d_pv + s0 : nullptr; P.ldcv = f->S; P.vec_family = f->vec_family;
+    P.out_mean = d_mean; P.out_var = d_var; P.status = d_status;
+    P.fac = f->d_fac + s0 * f->fac_ld; P.fac_ld = f->fac_ld; P.fac_mode = 2;
+    int launched = 0;
+    RC(predict_mma_launch(ctx, P, &launched));
+    if (!launched) { snprintf(ctx->err, sizeof(ctx->err), "ccgp_factors_predict: the stored factors no longer fit the kernel"); return CCGP_ERR_UNSUPPORTED; }
+    return CCGP_OK;
+}
+
+static void factors_free(ccgp_factors* f) {
+    if (!f) return;
+    for (ccgp_factors* c : f->child) factors_free(c);
+    if (f->owner && (f->d_pars || f->d_fac)) cudaSetDevice(f->owner->device);
+    if (f->d_pars) cudaFree(f->d_pars);
+    if (f->d_pv) cudaFree(f->d_pv);
+    if (f->d_fac) cudaFree(f->d_fac);
+    if (f->d_status) cudaFree(f->d_status);
+    delete f;
+}
+
+extern "C" int ccgp_factors_create(ccgp_ctx* ctx, int family, const double* pars, int64_t S, int64_t ldp, int vec_family,
+                                   const double* pars_vec, int64_t ldpv, ccgp_factors** out) {
+    if (!ctx) return CCGP_ERR_ARG;
+    ARG(out != nullptr);
+    *out = nullptr;
+    ARG(ctx->n > 0);
+    ARG(family >= 0 && family <= 4);
+    ARG(family < CCGP_MATERN1D || ctx->d == 1);
+    ARG(S >= 1 && ldp >= S && pars != nullptr);
+    ARG(pars_vec == nullptr || (vec_family >= 0 && vec_family <= 4 && ldpv >= S));
+    const int d = ctx->d, k = ccgp_num_params(family, d);
+    const int kv = pars_vec ? ccgp_num_params(vec_family, d) : 0;
+    ARG(k > 0 && kv >= 0);
+    ccgp_factors* f = new ccgp_factors();
+    f->owner = ctx; f->design_gen = ctx->design_gen; f->family = family; f->vec_family = pars_vec ? vec_family : -1;
+    f->k = k; f->kv = kv; f->S = S;
+    if (ctx->multi && S >= ccgp_num_gpus(ctx)) {
+        int rc = multi_factors_create(ctx, f, pars, ldp, pars_vec, ldpv);
+        if (rc) { factors_free(f); return rc; }
+        *out = f;
+        return CCGP_OK;
+    }
+    auto fail = [&](int rc) { factors_free(f); return rc; };
+#define CKF(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+        snprintf(ctx->err, sizeof(ctx->err), "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); return fail(CCGP_ERR_CUDA); } } while (0)
+    CKF(cudaSetDevice(ctx->device));
+    CKF(cudaMalloc(&f->d_pars, (size_t)S * k * 8));
+    if (kv) CKF(cudaMalloc(&f->d_pv, (size_t)S * kv * 8));
+    CKF(cudaMalloc(&f->d_status, (size_t)S * 4));
+    CKF(cudaMemcpy2DAsync(f->d_pars, (size_t)S * 8, pars, (size_t)ldp * 8, (size_t)S * 8, k, cudaMemcpyHostToDevice, ctx->stream));
+    if (kv) CKF(cudaMemcpy2DAsync(f->d_pv, (size_t)S * 8, pars_vec, (size_t)ldpv * 8, (size_t)S * 8, kv, cudaMemcpyHostToDevice, ctx->stream));
+    CKF(cudaMemsetAsync(f->d_status, 0, (size_t)S * 4, ctx->stream));
+    // Gaussian families on the tensor-path kernel keep their factors; everything else keeps the parameters only
+    if (family < CCGP_MATERN1D && (!pars_vec || vec_family < CCGP_MATERN1D) && !env_int("CCGP_PREDICT_OLD", 0) &&
+        !env_int("CCGP_FACTORS_OFF", 0)) {
+        PredictArgs P;
+        memset(&P, 0, sizeof(P));
+        FactorArgs& A = P.F;
+        A.lay = make_layout(ctx->n, 2);
+        f->fac_ld = (int64_t)A.lay.total + (int64_t)A.lay.NJ * 64 + 2;
+        if (cudaMalloc(&f->d_fac, (size_t)S * f->fac_ld * 8) != cudaSuccess) {
+            cudaGetLastError();                                   // out of memory: fall back to re-factoring
+            f->d_fac = nullptr;
+        } else {
+            A.d = d; A.design_mode = DESIGN_SHARED; memcpy(A.span2, ctx->span2, sizeof(A.span2)); A.twonu = ctx->twonu; A.mnorm = ctx->mnorm; A.X = ctx->d_X; A.y = ctx->d_y; A.n_designs = 1;
+            A.cand = f->d_pars; A.ldc = S; A.n_params = S; A.family = family; A.logscale = 0; A.sigma2 = 1.0; A.W = S;
+            A.out_mode = OUT_NLL;
+            P.T = 0; P.candv = f->d_pv; P.ldcv = S; P.vec_family = f->vec_family; P.status = f->d_status;
+            P.fac = f->d_fac; P.fac_ld = f->fac_ld; P.fac_mode = 1;
+            int launched = 0;
+            int rc = predict_mma_launch(ctx, P, &launched);
+            if (rc) return fail(rc);
+            if (launched) f->stored = 1;
+            else { cudaFree(f->d_fac); f->d_fac = nullptr; }
+        }
+    }
+    CKF(cudaStreamSynchronize(ctx->stream));
+#undef CKF
+    *out = f;
+    return CCGP_OK;
+}
+
+extern "C" int ccgp_factors_destroy(ccgp_ctx* ctx, ccgp_factors* f) {
+    if (!ctx) return CCGP_ERR_ARG;
+    if (!f) return CCGP_OK;
+    ARG(f->owner == ctx);
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    factors_free(f);
+    return CCGP_OK;
+}
+
+extern "C" int ccgp_factors_info(ccgp_ctx* ctx, const ccgp_factors* f, int64_t* rows, int* stored, int64_t* device_bytes) {
+    if (!ctx) return CCGP_ERR_ARG;
+    ARG(f != nullptr && f->owner == ctx);
+    int st = f->stored;
+    int64_t bytes = f->stored ? f->S * f->fac_ld * 8 : 0;
+    for (const ccgp_factors* c : f->child) { st = st || c->stored; bytes += c->stored ? c->S * c->fac_ld * 8 : 0; }
+    if (rows) *rows = f->S;
+    if (stored) *stored = st;
+    if (device_bytes) *device_bytes = bytes;
+    return CCGP_OK;
+}
+
+extern "C" int ccgp_factors_predict_dev(ccgp_ctx* ctx, const ccgp_factors* f, const double* d_Xnew, int64_t T, double sigma2,
+                                        double* d_mean, double* d_var, int32_t* d_status) {
+    if (!ctx) return CCGP_ERR_ARG;
+    ARG(f != nullptr && f->owner == ctx && f->child.empty());
+    ARG(f->design_gen == ctx->design_gen);                       // the design the factors were built on is still in place
+    ARG(T >= 0 && sigma2 > 0);
+    if (T == 0) return CCGP_OK;
+    ARG(d_Xnew && d_mean && d_var);
+    CK(cudaSetDevice(ctx->device));
+    return factors_predict_slice_dev(ctx, f, 0, f->S, d_Xnew, T, sigma2, d_mean, d_var, d_status);
+}
+
+extern "C" int ccgp_factors_predict(ccgp_ctx* ctx, const ccgp_factors* f, const double* Xnew, int64_t T, double sigma2,
+                                    double* out_mean, double* out_var, int32_t* out_status) {
+    if (!ctx) return CCGP_ERR_ARG;
+    ARG(f != nullptr && f->owner == ctx);
+    ARG(f->design_gen == ctx->design_gen);
+    ARG(T >= 0 && sigma2 > 0);
+    if (T == 0) return CCGP_OK;
+    ARG(Xnew && out_mean && out_var);
+    if (!f->child.empty()) return multi_factors_predict(ctx, f, Xnew, T, sigma2, out_mean, out_var, out_status);
+    CK(cudaSetDevice(ctx->device));
+    const int d = ctx->d;
+    const int64_t S = f->S;
+    size_t need = ((size_t)T * d + 2 * (size_t)T * S) * 8 + (size_t)S * 4;
+    RC(ensure_ws(ctx, need));
+    double* d_xn = (double*)ctx->ws;
+    double* d_mean = d_xn + (size_t)T * d;
+    double* d_var = d_mean + (size_t)T * S;
+    int32_t* d_status = (int32_t*)(d_var + (size_t)T * S);
+    CK(cudaMemcpyAsync(d_xn, Xnew, (size_t)T * d * 8, cudaMemcpyHostToDevice, ctx->stream));
+    // posterior rows in chunks, as ccgp_predict: the table of chunk i travels back while chunk i+1 is computed
+    int64_t nchunk = env_int("CCGP_PREDICT_CHUNKS", 0);
+    if (nchunk <= 0) nchunk = ((double)S * (double)T >= 131072.0 && S >= 64) ? 4 : 1;
+    RC(ensure_copy_stream(ctx));
+    const int64_t step = (S + nchunk - 1) / nchunk;
+    auto fetch = [&](int64_t s0, int64_t ns) -> int {
+        CK(cudaMemcpyAsync(out_mean + (size_t)T * s0, d_mean + (size_t)T * s0, (size_t)T * ns * 8, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        CK(cudaMemcpyAsync(out_var + (size_t)T * s0, d_var + (size_t)T * s0, (size_t)T * ns * 8, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        return 0;
+    };
+    auto pipeline = [&]() -> int {
+        int slot = 0;
+        int64_t prev_s0 = -1, prev_ns = 0;
+        for (int64_t s0 = 0; s0 < S; s0 += step, slot ^= 1) {
+            const int64_t ns = std::min(step, S - s0);
+            RC(factors_predict_slice_dev(ctx, f, s0, ns, d_xn, T, sigma2, d_mean + (size_t)T * s0, d_var + (size_t)T * s0, d_status + s0));
+            CK(cudaEventRecord(ctx->ev_kern[slot], ctx->stream));
+            if (prev_s0 >= 0) {
+                CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_kern[slot ^ 1], 0));
+                RC(fetch(prev_s0, prev_ns));
+            }
+            prev_s0 = s0; prev_ns = ns;
+        }
+        CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_kern[slot ^ 1], 0));
+        RC(fetch(prev_s0, prev_ns));
+        if (out_status) CK(cudaMemcpyAsync(out_status, d_status, (size_t)S * 4, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        return 0;
+    };
+    int rc = pipeline();
     cudaError_t e1 = cudaStreamSynchronize(ctx->copy_stream), e2 = cudaStreamSynchronize(ctx->stream);
     if (rc) return rc;
     CK(e1);

@@ -43,7 +43,24 @@ struct ccgp_ctx {
     int* sm_slots = nullptr;   // per-SM CTA arrival counters of the DMMA kernel
     double* last_bv_dev = nullptr;     // device results of the last argmin_columns call (value, index per column):
     long long* last_bi_dev = nullptr;  // what the multi-GPU front end feeds to the NCCL (min, index) all-reduce
+    uint64_t design_gen = 0;           // bumped by every ccgp_set_design that changes the design (ccgp_factors are tied to it)
     struct MultiCtx* multi = nullptr;  // multi.cu: set on the front context of ccgp_create_multi
+};
+
+// Cholesky factors of S posterior rows kept in HBM (ccgp_factors_*, include/ccgp.h): what `factors.frame` ([A]:572-592)
+// ships through a data.frame as R.Inv + factor vectors per row.
+struct ccgp_factors {
+    ccgp_ctx* owner = nullptr;
+    uint64_t design_gen = 0;
+    int family = 0, vec_family = -1, k = 0, kv = 0;
+    int64_t S = 0;
+    int stored = 0;                    // 1: factors in HBM (tensor-path kernel); 0: parameters only, every prediction re-factors
+    double* d_pars = nullptr;          // S x k
+    double* d_pv = nullptr;            // S x kv (parameters of the correlation vector when they differ, quirk Q2) or NULL
+    double* d_fac = nullptr;           // S rows of fac_ld doubles: L | inverse diagonal tiles | bad flag, pad
+    int32_t* d_status = nullptr;       // S
+    int64_t fac_ld = 0;
+    std::vector<ccgp_factors*> child;  // front context of ccgp_create_multi: one slice of rows per GPU
 };
 
 
@@ -97,6 +114,9 @@ int multi_nll_argmin(ccgp_ctx* front, int family, int scale, const double* cand,
 int multi_predict(ccgp_ctx* front, int family, const double* pars, int64_t S, int64_t ldp, int vec_family,
                   const double* pars_vec, int64_t ldpv, const double* Xnew, int64_t T, double sigma2, double* out_mean,
                   double* out_var, int32_t* out_status);
+int multi_factors_create(ccgp_ctx* front, ccgp_factors* f, const double* pars, int64_t ldp, const double* pars_vec, int64_t ldpv);
+int multi_factors_predict(ccgp_ctx* front, const ccgp_factors* f, const double* Xnew, int64_t T, double sigma2, double* out_mean,
+                          double* out_var, int32_t* out_status);
 int multi_me_schur_batch(ccgp_ctx* front, const double* D_old, int n_old, int d, const double* D_new, int n_new, int64_t C,
                          const double* params, int64_t P, int64_t ldq, double* out_negdet, double* out_logdet, int32_t* out_status);
 int multi_me_argmin(ccgp_ctx* front, const double* D_old, int n_old, int d, const double* D_new, int n_new, int64_t C,

@@ -183,6 +183,29 @@ int multi_predict(ccgp_ctx* front, int family, const double* pars, int64_t S, in
     });
 }
 
+// factors kept on the device (ccgp_factors_*): GPU g factors and keeps rows slice(S, g, G); predictions land in the
+// caller's column slices like multi_predict's
+int multi_factors_create(ccgp_ctx* front, ccgp_factors* f, const double* pars, int64_t ldp, const double* pars_vec, int64_t ldpv) {
+    const int G = front->multi->G;
+    f->child.assign(G, nullptr);
+    return fan_out(front, [&](int g) {
+        int64_t s0, ns;
+        slice(f->S, g, G, &s0, &ns);
+        return ccgp_factors_create(front->multi->child[g], f->family, pars + s0, ns, ldp, f->vec_family,
+                                   pars_vec ? pars_vec + s0 : nullptr, ldpv, &f->child[g]);
+    });
+}
+int multi_factors_predict(ccgp_ctx* front, const ccgp_factors* f, const double* Xnew, int64_t T, double sigma2, double* out_mean,
+                          double* out_var, int32_t* out_status) {
+    const int G = front->multi->G;
+    return fan_out(front, [&](int g) {
+        int64_t s0, ns;
+        slice(f->S, g, G, &s0, &ns);
+        return ccgp_factors_predict(front->multi->child[g], f->child[g], Xnew, T, sigma2, out_mean + (size_t)T * s0,
+                                    out_var + (size_t)T * s0, out_status ? out_status + s0 : nullptr);
+    });
+}
+
 // ---- the (min, index) all-reduce over NCCL ----------------------------------------------------------------------
 // per GPU, L slots: own best value (NaN / idx < 0 -> +inf) and own best GLOBAL index
 __global__ void multi_prepare_kernel(const double* bv, const long long* bi, long long offset, double* val, long long* idx, int64_t L) {

@@ -32,6 +32,12 @@ struct PredictArgs {
     double* out_mean;      // T x S column-major
     double* out_var;
     int32_t* status;       // S
+    // factors kept on the device (ccgp_factors_*, predict_mma_kernel only): per posterior row the factor L (fragment
+    // layout, lay.total doubles), the NJ inverse diagonal tiles (NJ * 64) and {bad flag, pad}
+    double* fac;           // row s at fac + s * fac_ld
+    int64_t fac_ld;
+    int fac_mode;          // 0: factor and predict; 1: factor, store, predict (T may be 0); 2: load the stored factor, predict
+    int t_chunks;          // mode 2: the sites of one row are split over this many CTAs (>= 1)
 };
 
 // extra shared doubles after the factor engine's block:

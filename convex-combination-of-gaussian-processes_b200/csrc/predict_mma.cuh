@@ -57,7 +57,11 @@ __global__ void __launch_bounds__(PM_NW * 32, 2) predict_mma_kernel(const Predic
     for (int i = tid; i < n; i += TEAM) ys[i] = A.y[i];
     const double* Ll = Ls + 2 * lane;
 
-    for (int64_t s = blockIdx.x; s < A.W; s += gridDim.x) {
+    const int nchunk = (P.fac_mode == 2 && P.t_chunks > 1) ? P.t_chunks : 1;
+    const int64_t rec_l = lay.total, rec_i = (int64_t)NJ * 64;
+    for (int64_t item = blockIdx.x; item < A.W * nchunk; item += gridDim.x) {
+        const int64_t s = item / nchunk;
+        const int chunk = (int)(item - s * nchunk);
         __syncthreads();
         if (tid == 0) load_params(A, s, prm);
         if (tid == 32) {
@@ -68,6 +72,16 @@ __global__ void __launch_bounds__(PM_NW * 32, 2) predict_mma_kernel(const Predic
             }
         }
         __syncthreads();
+        if (P.fac_mode == 2) {
+            // the stored factor of row s: L, the inverse diagonal tiles, the bad flag (ccgp_factors_create wrote them)
+            const double2* src = reinterpret_cast<const double2*>(P.fac + s * P.fac_ld);
+            double2* dl = reinterpret_cast<double2*>(Ls);
+            double2* di = reinterpret_cast<double2*>(linv_all);
+            for (int64_t e = tid; e < rec_l / 2; e += TEAM) dl[e] = src[e];
+            for (int64_t e = tid; e < rec_i / 2; e += TEAM) di[e] = src[rec_l / 2 + e];
+            if (tid == 0) red[62] = P.fac[s * P.fac_ld + rec_l + rec_i];
+            __syncthreads();
+        } else {
         // ---------------- phase 1: build + factor (factor_mma_kernel's schedule), all inverses kept ----------------
         if (prm->clamp) mma_build<DT, true>(A, Ls, Xs, ys, prm, etab, warp, NW, lane);
         else mma_build<DT, false>(A, Ls, Xs, ys, prm, etab, warp, NW, lane);
@@ -134,6 +148,15 @@ __global__ void __launch_bounds__(PM_NW * 32, 2) predict_mma_kernel(const Predic
                 __syncthreads();
             }
         }
+        if (P.fac_mode == 1) {                   // (every step of the factor loop ends in __syncthreads: L and the inverses are final)
+            double2* dst = reinterpret_cast<double2*>(P.fac + s * P.fac_ld);
+            const double2* sl = reinterpret_cast<const double2*>(Ls);
+            const double2* si = reinterpret_cast<const double2*>(linv_all);
+            for (int64_t e = tid; e < rec_l / 2; e += TEAM) dst[e] = sl[e];
+            for (int64_t e = tid; e < rec_i / 2; e += TEAM) dst[rec_l / 2 + e] = si[e];
+            if (tid == 0) { P.fac[s * P.fac_ld + rec_l + rec_i] = red[62]; P.fac[s * P.fac_ld + rec_l + rec_i + 1] = 0.0; }
+        }
+        }
         // ---------------- scalars: s11 = z_1.z_1, beta = z_1.z_y / s11 ----------------
         double s11 = 0.0, s1y = 0.0;
         for (int k = tid; k < n; k += TEAM) {
@@ -145,13 +168,16 @@ __global__ void __launch_bounds__(PM_NW * 32, 2) predict_mma_kernel(const Predic
         team_sum2<TEAM>(s11, s1y, red);
         const double beta = s1y / s11;
         const bool bad = red[62] != 0.0;
-        if (tid == 0 && P.status) P.status[s] = bad ? 1 : 0;
+        if (tid == 0 && P.status && chunk == 0) P.status[s] = bad ? 1 : 0;
 
         // ---------------- phase 2: sites, 16 per warp and pass ----------------
         double* vb = vbuf_all + (size_t)warp * PM_G * NJ * 64;
         const bool clampv = prmv->clamp != 0 || true;      // sites may lie anywhere: always the clamped exponential
         const double rho = prmv->rho, ca = prmv->a, cb = prmv->b;
-        for (int64_t t0 = (int64_t)warp * (8 * PM_G); t0 < P.T; t0 += (int64_t)NW * 8 * PM_G) {
+        // this CTA's share of the sites: groups of 8 * PM_G, chunk `chunk` of `nchunk`
+        const int64_t ngrp = (P.T + 8 * PM_G - 1) / (8 * PM_G);
+        const int64_t g_lo = ngrp * chunk / nchunk, g_hi = ngrp * (chunk + 1) / nchunk;
+        for (int64_t t0 = (g_lo + warp) * (8 * PM_G); t0 < g_hi * (8 * PM_G); t0 += (int64_t)NW * 8 * PM_G) {
             double xs[PM_G][DT > 0 ? DT : MAXD];
 #pragma unroll
             for (int g = 0; g < PM_G; ++g) {

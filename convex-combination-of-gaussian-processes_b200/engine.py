@@ -215,6 +215,16 @@ class Engine:
                                         _ptr(X_new), T, float(sigma2), _ptr(mean), _ptr(var), _ptr(status)))
         return mean, var, status
 
+    def factors(self, pars, family, pars_vec=None, vec_family=-1):
+        """Factor the S posterior rows once and keep the factors in HBM (ccgp_factors_create): the device-side
+        `factors.frame` ([A]:572-592).  -> `Factors`, whose predict(X_new, sigma2) returns what `predict` returns."""
+        pars = _f(np.atleast_2d(pars))
+        S = pars.shape[0]
+        pv = None if pars_vec is None else _f(np.atleast_2d(pars_vec))
+        h = C.c_void_p()
+        self._ck(self._lib.ccgp_factors_create(self._h, family, _ptr(pars), S, S, vec_family, _ptr(pv), S, C.byref(h)))
+        return Factors(self, h, S)
+
     # -- ME criteria --------------------------------------------------------------
     @staticmethod
     def _pack_designs(D_new):
@@ -371,3 +381,46 @@ class Engine:
         out = np.empty((na, nb), order="F")
         self._ck(self._lib.ccgp_mixed_corr(self._h, family, _ptr(params), _ptr(A), na, _ptr(Bm), nb, d, _ptr(out)))
         return out
+
+
+class Factors:
+    """Cholesky factors of S posterior rows resident on the device (ccgp_factors_*, include/ccgp.h), keyed by row index."""
+
+    def __init__(self, engine, handle, S):
+        self._eng, self._h, self.S = engine, handle, S
+
+    def info(self):
+        rows, stored, nbytes = C.c_int64(), C.c_int(), C.c_int64()
+        self._eng._ck(self._eng._lib.ccgp_factors_info(self._eng._h, self._h, C.byref(rows), C.byref(stored), C.byref(nbytes)))
+        return dict(rows=rows.value, stored=bool(stored.value), device_bytes=nbytes.value)
+
+    def predict(self, X_new, sigma2):
+        """-> (mean[T,S], var[T,S], status[S]) at the sites X_new, from the stored factors."""
+        X_new = _f(np.atleast_2d(X_new))
+        T, S = X_new.shape[0], self.S
+        if X_new.shape[1] != self._eng.d:
+            raise ValueError("X_new has %d columns, design has %d" % (X_new.shape[1], self._eng.d))
+        mean = np.empty((T, S), order="F")
+        var = np.empty((T, S), order="F")
+        status = np.empty(S, dtype=np.int32)
+        self._eng._ck(self._eng._lib.ccgp_factors_predict(self._eng._h, self._h, _ptr(X_new), T, float(sigma2),
+                                                          _ptr(mean), _ptr(var), _ptr(status)))
+        return mean, var, status
+
+    def predict_dev(self, Xnew_t, sigma2, out_mean, out_var, out_status=None):
+        """torch CUDA tensors (Xnew_t d x T row-major, out_* T*S); single-GPU contexts.  Async."""
+        d, T = Xnew_t.shape
+        self._eng._ck(self._eng._lib.ccgp_factors_predict_dev(self._eng._h, self._h, Xnew_t.data_ptr(), T, float(sigma2),
+                                                              out_mean.data_ptr(), out_var.data_ptr(),
+                                                              out_status.data_ptr() if out_status is not None else None))
+
+    def close(self):
+        if getattr(self, "_h", None) and getattr(self._eng, "_h", None):
+            self._eng._lib.ccgp_factors_destroy(self._eng._h, self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

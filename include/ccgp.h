@@ -152,6 +152,27 @@ int ccgp_predict_dev(ccgp_ctx* ctx, int family, const double* d_pars, int64_t S,
                      const double* d_Xnew, int64_t T, double sigma2,
                      double* d_mean, double* d_var, int32_t* d_status);
 
+/* ---- factors kept on the device: factors.frame [A]:572-592 + prediction [A]:637-654
+ * The reference factors every posterior row once (`factors`, [A]:550-559), ships R.Inv, beta and the factor vectors
+ * through a data.frame (n^2 + 2n + 5 doubles per row, [A]:587-591) and lets `prediction` walk rows x sites.  Here the
+ * per-row state is the Cholesky factor, kept in HBM and keyed by the row index (= sample id):
+ *   ccgp_factors_create   factors the S rows of `pars` (same arguments as ccgp_predict) on the design in place;
+ *   ccgp_factors_predict  the T x S tables at new sites from the stored factors (only the site phase runs; values are
+ *                         bit-identical to ccgp_predict on the same rows), any number of times;
+ *   ccgp_factors_info     rows, whether the factors are stored (Gaussian families within the shared-memory kernel;
+ *                         otherwise only the parameters are kept and every prediction re-factors), bytes of HBM held;
+ *   ccgp_factors_destroy  releases them.  A ccgp_set_design with a different design invalidates the object
+ *                         (CCGP_ERR_ARG from predict).  On a ccgp_create_multi context the rows are split over the GPUs. */
+typedef struct ccgp_factors ccgp_factors;
+int ccgp_factors_create(ccgp_ctx* ctx, int family, const double* pars, int64_t S, int64_t ldp,
+                        int vec_family, const double* pars_vec, int64_t ldpv, ccgp_factors** out);
+int ccgp_factors_predict(ccgp_ctx* ctx, const ccgp_factors* f, const double* Xnew, int64_t T, double sigma2,
+                         double* out_mean, double* out_var, int32_t* out_status);
+int ccgp_factors_predict_dev(ccgp_ctx* ctx, const ccgp_factors* f, const double* d_Xnew, int64_t T, double sigma2,
+                             double* d_mean, double* d_var, int32_t* d_status);
+int ccgp_factors_info(ccgp_ctx* ctx, const ccgp_factors* f, int64_t* rows, int* stored, int64_t* device_bytes);
+int ccgp_factors_destroy(ccgp_ctx* ctx, ccgp_factors* f);
+
 /* ---- maximum-entropy design criteria -------------------------------------
  * ccgp_me_schur_batch: Augmented.Mixed.Entropy [M]:869-877 for C candidate
  * second-batch designs x P parameter rows (GAUSS_ISO rows (p,theta1,theta2),

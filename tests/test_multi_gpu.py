@@ -64,6 +64,12 @@ def test_multi_sweep_and_predict_match_single(engine, multi, designs):
     ma, va, _ = engine.predict(pars, GAUSS_ISO, designs["he_test"][:, :4], 30.0)
     mb, vb, _ = multi.predict(pars, GAUSS_ISO, designs["he_test"][:, :4], 30.0)
     assert np.array_equal(ma, mb) and np.array_equal(va, vb)
+    # factors kept on the device (ccgp_factors_*): rows sliced over the GPUs, same tables
+    fac = multi.factors(pars, GAUSS_ISO)
+    assert fac.info()["stored"] and fac.info()["rows"] == len(pars)
+    mc, vc, _ = fac.predict(designs["he_test"][:, :4], 30.0)
+    assert np.array_equal(ma, mc) and np.array_equal(va, vc)
+    fac.close()
 
 
 def test_multi_me_argmin_both_splits(engine, multi):
