@@ -134,6 +134,7 @@ extern "C" int ccgp_destroy(ccgp_ctx* ctx) {
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->ws2) cudaFree(ctx->ws2);
     if (ctx->sm_slots) cudaFree(ctx->sm_slots);
+    if (ctx->fac_scratch) cudaFree(ctx->fac_scratch);
     ctx->big.release();
     if (ctx->copy_stream) {
         cudaStreamDestroy(ctx->copy_stream);
@@ -693,6 +694,23 @@ static int predict_mma_launch(ccgp_ctx* ctx, PredictArgs& P, int* launched) {
     if (nb < 1) return 0;
     const int64_t slots = (int64_t)nb * ctx->num_sm;
     P.t_chunks = 1;
+    if (P.fac_mode == 0 && A.W * 2 <= slots && P.T >= 128 && !env_int("CCGP_PREDICT_NOSPLIT", 0)) {
+        // few posterior rows, many sites (the plug-in / posterior-mean surface over a grid): factor the rows into a scratch
+        // buffer, then run the site phase with the sites of a row split over the idle CTAs -- same values, two launches
+        const int64_t fac_ld = (int64_t)l.total + (int64_t)l.NJ * 64 + 2;
+        const size_t need = (size_t)A.W * fac_ld * 8;
+        if (need > ctx->fac_scratch_bytes) {
+            if (ctx->fac_scratch) { CK(cudaFree(ctx->fac_scratch)); ctx->fac_scratch = nullptr; ctx->fac_scratch_bytes = 0; }
+            CK(cudaMalloc(&ctx->fac_scratch, need));
+            ctx->fac_scratch_bytes = need;
+        }
+        PredictArgs Q = P;
+        Q.fac = ctx->fac_scratch; Q.fac_ld = fac_ld; Q.fac_mode = 1; Q.T = 0;
+        fn<<<(unsigned)A.W, PM_NW * 32, smem, ctx->stream>>>(Q);
+        CK(cudaGetLastError());
+        ctx->launches++;
+        P.fac = ctx->fac_scratch; P.fac_ld = fac_ld; P.fac_mode = 2;
+    }
     if (P.fac_mode == 2 && A.W < slots) {
         // stored factors, fewer rows than resident CTAs: the sites of a row are split over several CTAs (64 sites = one pass
         // of the four warps is the smallest useful share)

@@ -43,6 +43,8 @@ struct ccgp_ctx {
     int* sm_slots = nullptr;   // per-SM CTA arrival counters of the DMMA kernel
     double* last_bv_dev = nullptr;     // device results of the last argmin_columns call (value, index per column):
     long long* last_bi_dev = nullptr;  // what the multi-GPU front end feeds to the NCCL (min, index) all-reduce
+    double* fac_scratch = nullptr;     // ccgp_predict with few rows and many sites: factors of the rows between its two launches
+    size_t fac_scratch_bytes = 0;
     uint64_t design_gen = 0;           // bumped by every ccgp_set_design that changes the design (ccgp_factors are tied to it)
     struct MultiCtx* multi = nullptr;  // multi.cu: set on the front context of ccgp_create_multi
 };

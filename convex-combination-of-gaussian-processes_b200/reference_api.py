@@ -219,6 +219,26 @@ def predict_post_batch(D_new, D_train, y_train, pars, sigma2, script="A", engine
     return mean, var
 
 
+def factors_device(D_train, y_train, pars, script="A", engine=None):
+    """`factors.frame` ([A]:572-592) without its wire format: factor the S posterior rows once and keep the Cholesky
+    factors on the device, keyed by the row index (Engine.factors -> ccgp_factors_create).  The returned object's
+    predict(D_new, sigma2) gives the tables of `predict_post_batch` for any number of site sets (bit-identical)."""
+    eng = engine or default_engine()
+    eng.set_design(D_train, y_train)
+    pars = np.atleast_2d(np.asarray(pars, dtype=np.float64))
+    family = _SCRIPT_FAMILY[script]
+    if family == GAUSS_ISO_RAW2:                       # quirk Q2 ([V]:672)
+        pv = np.column_stack([pars[:, 0], pars[:, 1], pars[:, 1] * (1.0 + pars[:, 2])])
+        return eng.factors(pars, GAUSS_ISO_RAW2, pars_vec=pv, vec_family=GAUSS_ISO)
+    return eng.factors(pars, family)
+
+
+def predict_post_factors(ff, D_new, sigma2):
+    """(mean[T,S], var[T,S]) at the sites D_new from the factors `factors_device` left on the device."""
+    mean, var, _ = ff.predict(D_new, sigma2)
+    return mean, var
+
+
 def predict_post(x_new, D_train, y_train, pars, sigma2, script="A", engine=None):
     """`predict.post(x.new, D.train, pars, sigma2)` -> cbind(mean, var) (1 x 2)."""
     m, v = predict_post_batch(np.asarray(x_new, dtype=np.float64).reshape(1, -1), D_train, y_train,

@@ -186,6 +186,25 @@ predict.post.batch <- function(D.new, D.train, y.train, pars, sigma2, nu = NULL)
   list(mean = r[[1]], var = r[[2]])
 }
 
+# factors.frame ([A]:572-592) without its wire format: factor every posterior row ONCE, keep the factors on the device
+# (HBM, keyed by the row index), predict at any number of site sets from them.  `pars` as in predict.post.batch.
+#   ff <- factors.device(D.train, y.train, pars.frame)
+#   tab <- predict.post.factors(ff, D.new, sigma2)     # list(mean, var), each T x S, identical to predict.post.batch
+factors.device <- function(D.train, y.train, pars, nu = NULL) {
+  cfg <- .ccgp$cfg
+  .ccgp.design(D.train, y.train); .ccgp.nu(nu)
+  k <- if (cfg$family == 1L) ncol(as.matrix(D.train)) + 2L else 3L
+  P <- matrix(as.double(as.matrix(pars)[, 1:k, drop = FALSE]), ncol = k)
+  pv <- NULL; vf <- -1L
+  if (cfg$script == "V") { pv <- cbind(P[, 1], P[, 2], P[, 2] * (1 + P[, 3])); vf <- 0L }   # [V]:672
+  .Call("ccgp_R_factors_create", .ccgp$ctx, cfg$family, P, vf, pv)
+}
+predict.post.factors <- function(ff, D.new, sigma2) {
+  r <- .Call("ccgp_R_factors_predict", .ccgp$ctx, ff, matrix(as.double(as.matrix(D.new)), nrow = nrow(as.matrix(D.new))), as.double(sigma2))
+  list(mean = r[[1]], var = r[[2]])
+}
+factors.release <- function(ff) invisible(.Call("ccgp_R_factors_release", ff))
+
 # t(apply_pb(D.new, 1, prediction, alpha, code, pars.frame, D.train, sigma2)) ([A]:685) from ONE predictive table:
 # per site the same statements as `prediction` ([A]:644-653): mean of means, rnorm draws, quantiles.
 prediction.table <- function(D.new, alpha, pars.frame, D.train, y.train, sigma2, nu = NULL, drop.negative.var = FALSE) {

@@ -133,6 +133,56 @@ SEXP ccgp_R_predict(SEXP ptr, SEXP family, SEXP pars, SEXP vec_family, SEXP pars
     return out;
 }
 
+/* ---- factors kept on the device: factors.frame [A]:572-592 without its wire format ----
+ * The handle is an external pointer that keeps the context's external pointer alive in its `prot` slot, so the
+ * context cannot be finalized first; its own finalizer releases the HBM. */
+static void factors_finalizer(SEXP ptr) {
+    ccgp_factors* f = (ccgp_factors*)R_ExternalPtrAddr(ptr);
+    SEXP cptr = R_ExternalPtrProtected(ptr);
+    if (f && cptr != R_NilValue) {
+        ccgp_ctx* ctx = (ccgp_ctx*)R_ExternalPtrAddr(cptr);
+        if (ctx) ccgp_factors_destroy(ctx, f);
+    }
+    R_ClearExternalPtr(ptr);
+}
+
+/* pars: S x k, pars_vec: S x k' or NULL.  Returns the factors handle. */
+SEXP ccgp_R_factors_create(SEXP ptr, SEXP family, SEXP pars, SEXP vec_family, SEXP pars_vec) {
+    ccgp_ctx* ctx = get_ctx(ptr);
+    int64_t S = Rf_nrows(pars);
+    const double* pv = Rf_isNull(pars_vec) ? NULL : REAL(pars_vec);
+    ccgp_factors* f = NULL;
+    int rc = ccgp_factors_create(ctx, Rf_asInteger(family), REAL(pars), S, S, Rf_asInteger(vec_family), pv, S, &f);
+    check(ctx, rc, "factors_create");
+    SEXP out = PROTECT(R_MakeExternalPtr(f, R_NilValue, ptr));
+    R_RegisterCFinalizerEx(out, factors_finalizer, TRUE);
+    UNPROTECT(1);
+    return out;
+}
+
+/* Xnew: T x d.  Returns list(mean (T x S), var (T x S), status) from the stored factors. */
+SEXP ccgp_R_factors_predict(SEXP ptr, SEXP fptr, SEXP Xnew, SEXP sigma2) {
+    ccgp_ctx* ctx = get_ctx(ptr);
+    ccgp_factors* f = (ccgp_factors*)R_ExternalPtrAddr(fptr);
+    if (!f) Rf_error("ccgp: factors already released");
+    int64_t S = 0, T = Rf_nrows(Xnew);
+    check(ctx, ccgp_factors_info(ctx, f, &S, NULL, NULL), "factors_info");
+    SEXP mean = PROTECT(Rf_allocMatrix(REALSXP, (int)T, (int)S));
+    SEXP var = PROTECT(Rf_allocMatrix(REALSXP, (int)T, (int)S));
+    SEXP status = PROTECT(Rf_allocVector(INTSXP, S));
+    int rc = ccgp_factors_predict(ctx, f, REAL(Xnew), T, Rf_asReal(sigma2), REAL(mean), REAL(var), (int32_t*)INTEGER(status));
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 3));
+    SET_VECTOR_ELT(out, 0, mean); SET_VECTOR_ELT(out, 1, var); SET_VECTOR_ELT(out, 2, status);
+    UNPROTECT(4);
+    check(ctx, rc, "factors_predict");
+    return out;
+}
+
+SEXP ccgp_R_factors_release(SEXP fptr) {
+    factors_finalizer(fptr);
+    return R_NilValue;
+}
+
 /* D.old: n_old x d (or NULL), D.new: (n_new*d) x C matrix whose columns are c(D.new) vectors,
  * params: P x 3.  Returns list(negdet (C x P), logdet (C x P), status (C x P)). */
 SEXP ccgp_R_me_schur_batch(SEXP ptr, SEXP D_old, SEXP D_new, SEXP n_new_, SEXP d_, SEXP params) {
@@ -326,6 +376,9 @@ static const R_CallMethodDef ccgp_call_methods[] = {
     CALLDEF(ccgp_R_rinv_batch, 5),
     CALLDEF(ccgp_R_rcond_batch, 4),
     CALLDEF(ccgp_R_predict, 7),
+    CALLDEF(ccgp_R_factors_create, 5),
+    CALLDEF(ccgp_R_factors_predict, 4),
+    CALLDEF(ccgp_R_factors_release, 1),
     CALLDEF(ccgp_R_me_schur_batch, 6),
     CALLDEF(ccgp_R_me_argmin, 6),
     CALLDEF(ccgp_R_me_schur_paired, 7),

@@ -36,6 +36,7 @@ SEXP SET_VECTOR_ELT(SEXP, R_xlen_t, SEXP);
 SEXP R_MakeExternalPtr(void*, SEXP, SEXP);
 void* R_ExternalPtrAddr(SEXP);
 void R_ClearExternalPtr(SEXP);
+SEXP R_ExternalPtrProtected(SEXP);
 typedef void (*R_CFinalizer_t)(SEXP);
 void R_RegisterCFinalizerEx(SEXP, R_CFinalizer_t, Rboolean);
 void Rf_error(const char*, ...) __attribute__((noreturn, format(printf, 1, 2)));

@@ -6,6 +6,7 @@ import os
 import numpy as np
 import pytest
 
+from ccgp_b200 import reference_api as api
 from ccgp_b200 import CcgpError, GAUSS_ANISO_LAMBDA, GAUSS_ISO, GAUSS_ISO_RAW2, MATERN1D, workloads
 from conftest import rel_err
 
@@ -68,11 +69,39 @@ def test_stored_factors_golden_tables(engine, golden, designs):
     fac.close()
     he, het = designs["he_train"], designs["he_test"]
     engine.set_design(he[:, :4], he[:, 4])
-    fac = engine.factors(golden["predHE_pars"], GAUSS_ISO)
-    m, v, _ = fac.predict(het[:, :4], 30.0)
+    fac = api.factors_device(he[:, :4], he[:, 4], golden["predHE_pars"], script="H", engine=engine)
+    m, v = api.predict_post_factors(fac, het[:, :4], 30.0)
     assert rel_err(m, golden["predHE_mean"]).max() < TOL
     assert np.abs(v - golden["predHE_var"]).max() / 30.0 < TOL
     fac.close()
+    # quirk Q2 ([V]:672): the matrix rows use `lambda`, the vector theta1 (1 + lambda)
+    fac = api.factors_device(designs["maximin14"], golden["pred14_y"], golden["predV_pars"], script="V", engine=engine)
+    m, v = api.predict_post_factors(fac, golden["pred14_Xnew"], 0.9)
+    assert rel_err(m, golden["predV_mean"]).max() < TOL
+    assert np.abs(v - golden["predV_var"]).max() < TOL * 0.9
+    fac.close()
+
+
+def test_few_rows_many_sites_split_over_ctas(engine):
+    """ccgp_predict with few posterior rows and many sites factors into a scratch buffer and splits the sites of a row over
+    the idle CTAs (two launches): same values as the one-launch path (CCGP_PREDICT_NOSPLIT=1), bit for bit."""
+    rng = np.random.default_rng(77)
+    X, y, _ = workloads.m1_design()
+    engine.set_design(X, y)
+    for S, T in ((1, 625), (5, 2000), (40, 130)):
+        pars = _pars(rng, GAUSS_ANISO_LAMBDA, S, 100, 2)
+        g = rng.uniform(-1, 1, (T, 2))
+        l0 = engine.launch_count
+        a = engine.predict(pars, GAUSS_ANISO_LAMBDA, g, 1.7)
+        assert engine.launch_count - l0 == 2
+        os.environ["CCGP_PREDICT_NOSPLIT"] = "1"
+        try:
+            l0 = engine.launch_count
+            b = engine.predict(pars, GAUSS_ANISO_LAMBDA, g, 1.7)
+            assert engine.launch_count - l0 == 1
+        finally:
+            os.environ.pop("CCGP_PREDICT_NOSPLIT", None)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
 
 
 def test_factors_fall_back_to_refactoring(engine):
