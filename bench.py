@@ -436,6 +436,29 @@ def run_ours(args, rank, world, local_rank):
                              "note": "frac: SURVEY 8(d) count of the reference's explicit-inverse algorithm (2 n^2 per site); "
                                      "frac_executed: the forward-solve algorithm the kernel runs (n^2 per site); 2 n exp per site in neither"},
                 "finite": bool(torch.isfinite(pm).all().item())}
+        # the same table from factors kept on the device (ccgp_factors_*: the device-side factors.frame): site phase only
+        fac = eng.factors(nat_p, GAUSS_ANISO_LAMBDA)
+        pm2 = torch.empty_like(pm)
+        pv2 = torch.empty_like(pvv)
+        for _ in range(3):
+            fac.predict_dev(d_xn, s2, pm2, pv2)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(me_steps):
+            fac.predict_dev(d_xn, s2, pm2, pv2)
+        e1.record(stream)
+        barrier()
+        f_ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([f_ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            f_ms = float(t.item())
+        finfo = fac.info()
+        pred["from_stored_factors"] = {"value": world * S_p * T_p * me_steps / (f_ms * 1e-3), "unit": "pairs/s", "ms_per_step": f_ms / me_steps,
+                                       "device_bytes": finfo["device_bytes"], "stored": finfo["stored"],
+                                       "bit_identical_to_direct": bool(torch.equal(pm, pm2) and torch.equal(pvv, pv2))}
+        fac.close()
         # ---- large-n blocked FP64-tensor path (north_star: synthetic n = 2048, 2-D anisotropic; SURVEY 8d ME-B(1)), rank 0
         if rank == 0:
             n_big, B_big = 2048, 64
