@@ -16,7 +16,9 @@
 // CCGP_BIG_RIGHT=1 runs the first version of this path (right-looking: potrf, big_trsm_kernel, one K = 64
 // big_syrk_kernel launch per panel) for A/B timing.
 // Row layout: [0,n) design points, [n,ncp) identity padding (ncp = n rounded up to 64),
-// rows ncp and ncp+1 are y' and 1', zero rows up to nrp = ncp + 64.
+// rows ncp and ncp+1 are y' and 1', zero rows up to nrp = ncp + 8 (ncp + 64 under CCGP_BIG_RIGHT: the first version's
+// kernels work on 64-row tiles): the update kernel's last row tile then holds 8 or 72 rows and its warps skip the
+// quadrants beyond them, instead of multiplying 64 rows of padding per block column.
 #pragma once
 #include <algorithm>
 #include <stdlib.h>
@@ -53,8 +55,9 @@ __global__ void __launch_bounds__(256) big_build_kernel(BigArgs G) {
     const int b = blockIdx.z, ti = blockIdx.y, tj = blockIdx.x;
     if (ti < tj) return;
     const Prm* pr = G.prm + b;
-    __shared__ double xi[MAXD][64], xj[MAXD][64], wts[MAXD];
+    __shared__ double xi[MAXD][64], xj[MAXD][64], wts[MAXD], etab[128];
     const int tid = threadIdx.x, n = G.n, d = G.d;
+    if (tid < 128) etab[tid] = CCGP_EXP2_TAB[tid];
     for (int e = tid; e < d * 64; e += 256) {
         int k = e / 64, r = e % 64;
         int i = ti * 64 + r, j = tj * 64 + r;
@@ -73,13 +76,14 @@ __global__ void __launch_bounds__(256) big_build_kernel(BigArgs G) {
     for (int e = tid; e < 64 * 64; e += 256) {
         const int r = e % 64, c = e / 64;
         const int i = ti * 64 + r, j = tj * 64 + c;
+        if (i >= G.nrp) continue;                         // (the tile of the extra rows is 8 rows tall)
         double v = 0.0;
         if (i < n && j < n) {
             if (i == j) v = 1.0;
             else if (i > j) {
                 double s1 = 0.0;
                 for (int k = 0; k < d; ++k) { double df = xi[k][r] - xj[k][c]; s1 = fma(wts[k] * df, df, s1); }
-                v = fma(bb, dexp_neg_dev<true>(rho * s1), a * dexp_neg_dev<true>(s1));
+                v = fma(bb, dexp_neg_tab_dev<true>(rho * s1, etab), a * dexp_neg_tab_dev<true>(s1, etab));
             }
         } else if (i == j) v = 1.0;                       // identity padding (i, j in [n, ncp))
         else if (j < n && i == G.ncp) v = G.y ? G.y[j] : 0.0;   // row y' (absent in determinant mode)
@@ -341,8 +345,7 @@ __global__ void __launch_bounds__(128) big_syrk_kernel(BigArgs G, int k, int nti
 // 32-column chunks with cp.async, double buffered (the chunk after next is in flight while this one is
 // multiplied); k-major staging with leading dimensions 136 / 72 (k-stride = 64 B mod 128 B) keeps every fragment
 // load conflict-free.
-constexpr int BU_KC = 32, BU_LDA = 136, BU_LDB = 72;
-constexpr int BU_STAGE = BU_KC * (BU_LDA + BU_LDB);           // doubles per stage
+constexpr int BU_KC = 32, BU_LDB = 72;
 __device__ __forceinline__ void cp_async16(double* dst_smem, const double* src) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
@@ -351,12 +354,19 @@ __device__ __forceinline__ void cp_async16(double* dst_smem, const double* src) 
 // chlo, chhi: the 32-column chunks of the contraction this launch covers (update mode: panels chlo/2 .. chhi/2 - 1 -- the
 // lookahead splits a column's update into "everything but the last panel", launched early on a side stream, and the last
 // panel; TRSM mode: 0, 2).
-template <bool TRSM>
-__global__ void __launch_bounds__(256, 2) big_update_kernel(BigArgs G, int k, int chlo, int chhi) {
+// ROWS = 128: 8 warps as 4 x 2 quadrants of 32 x 32; ROWS = 64: 2 x 4 pieces of 32 x 16 -- half the work per CTA, chosen by
+// the host for block columns whose 128-row tiles would leave most SMs idle in the last round (big_update_rows).
+template <int ROWS> __host__ __device__ constexpr int bu_lda() { return ROWS + 8; }           // leading dimension of the staged A chunk (k-stride = 64 B mod 128 B)
+template <int ROWS> __host__ __device__ constexpr int bu_stage() { return BU_KC * (bu_lda<ROWS>() + BU_LDB); }
+template <bool TRSM, int ROWS>
+__global__ void __launch_bounds__(256, ROWS == 128 ? 2 : 3) big_update_kernel(BigArgs G, int k, int chlo, int chhi) {
+    static_assert(ROWS == 128 || ROWS == 64, "ROWS");
+    constexpr int NJF = ROWS == 128 ? 4 : 2;                          // 8-column fragments per warp
+    constexpr int BU_LDA = bu_lda<ROWS>(), BU_STAGE = bu_stage<ROWS>();
     extern __shared__ __align__(16) double sm[];
     const int b = blockIdx.y, tid = threadIdx.x;
-    const int row0 = (TRSM ? (k + 1) * 64 : k * 64) + blockIdx.x * 128;   // first row of this tile
-    const int rows_here = min(128, G.nrp - row0);                     // 128 or 64
+    const int row0 = (TRSM ? (k + 1) * 64 : k * 64) + blockIdx.x * ROWS;  // first row of this tile
+    const int rows_here = min(ROWS, G.nrp - row0);                    // ROWS, or 72 / 8 in the last tile (64 with the old layout)
     const double* Ab = G.A + (size_t)b * G.stride;
     const int nch = chhi - chlo;                                      // 32-column chunks: panels of the range, or block column k itself
     const double* Lt = G.linv + (size_t)b * 4096;
@@ -364,8 +374,8 @@ __global__ void __launch_bounds__(256, 2) big_update_kernel(BigArgs G, int k, in
         double* As = sm + stage * BU_STAGE;
         double* Bs = As + BU_KC * BU_LDA;
         const size_t col0 = (size_t)(chlo + ch) * BU_KC + (TRSM ? (size_t)k * 64 : 0);
-        for (int e = tid; e < BU_KC * 64; e += 256) {                 // A: 32 columns x 64 chunks of 2 rows
-            const int kk = e >> 6, r2 = (e & 63) * 2;
+        for (int e = tid; e < BU_KC * (ROWS / 2); e += 256) {         // A: 32 columns x ROWS / 2 chunks of 2 rows
+            const int kk = e / (ROWS / 2), r2 = (e % (ROWS / 2)) * 2;
             double* dst = As + kk * BU_LDA + r2;
             if (r2 < rows_here) cp_async16(dst, Ab + (col0 + kk) * G.nrp + row0 + r2);
             else { dst[0] = 0.0; dst[1] = 0.0; }
@@ -378,13 +388,14 @@ __global__ void __launch_bounds__(256, 2) big_update_kernel(BigArgs G, int k, in
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
     const int warp = tid >> 5, lane = tid & 31;
-    const int wr = (warp >> 1) * 32, wc = (warp & 1) * 32;
+    const int wr = (ROWS == 128 ? (warp >> 1) : (warp >> 2)) * 32, wc = ROWS == 128 ? (warp & 1) * 32 : (warp & 3) * 16;
     const int fr = lane >> 2, fk = lane & 3;
-    double acc[4][4][2];
+    const int nfrag = min(4, max(0, (rows_here - wr + 7) >> 3));     // live 8-row fragment rows of this warp's 32 rows
+    double acc[4][NJF][2];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+        for (int j = 0; j < NJF; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
     load(0, 0);
     for (int ch = 0; ch < nch; ++ch) {
         if (ch + 1 < nch) {
@@ -396,17 +407,34 @@ __global__ void __launch_bounds__(256, 2) big_update_kernel(BigArgs G, int k, in
         __syncthreads();
         const double* As = sm + (ch & 1) * BU_STAGE;
         const double* Bs = As + BU_KC * BU_LDA;
+        if (nfrag == 4) {
 #pragma unroll
-        for (int k0 = 0; k0 < BU_KC; k0 += 4) {
-            double af[4], bf[4];
+            for (int k0 = 0; k0 < BU_KC; k0 += 4) {
+                double af[4], bf[NJF];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) af[i] = As[(k0 + fk) * BU_LDA + wr + 8 * i + fr];
+                for (int i = 0; i < 4; ++i) af[i] = As[(k0 + fk) * BU_LDA + wr + 8 * i + fr];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) bf[j] = Bs[(k0 + fk) * BU_LDB + wc + 8 * j + fr];
+                for (int j = 0; j < NJF; ++j) bf[j] = Bs[(k0 + fk) * BU_LDB + wc + 8 * j + fr];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+                for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+                    for (int j = 0; j < NJF; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+            }
+        } else if (nfrag > 0) {                          // the last tile's partial piece: 8 live rows per fragment row
+#pragma unroll
+            for (int k0 = 0; k0 < BU_KC; k0 += 4) {
+                double bf[NJF];
+#pragma unroll
+                for (int j = 0; j < NJF; ++j) bf[j] = Bs[(k0 + fk) * BU_LDB + wc + 8 * j + fr];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (i < nfrag) {                     // warp-uniform
+                        const double af = As[(k0 + fk) * BU_LDA + wr + 8 * i + fr];
+#pragma unroll
+                        for (int j = 0; j < NJF; ++j) dmma884(acc[i][j][0], acc[i][j][1], af, bf[j]);
+                    }
+                }
+            }
         }
         __syncthreads();
     }
@@ -416,7 +444,7 @@ __global__ void __launch_bounds__(256, 2) big_update_kernel(BigArgs G, int k, in
         const int r = wr + 8 * i + fr;
         if (r < rows_here) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < NJF; ++j) {
                 const int c = wc + 8 * j + 2 * fk;
                 if (TRSM) {
                     C[(size_t)c * G.nrp + r] = acc[i][j][0];
@@ -428,6 +456,22 @@ __global__ void __launch_bounds__(256, 2) big_update_kernel(BigArgs G, int k, in
             }
         }
     }
+}
+// Rows per tile.  64-row tiles measured faster than 128-row tiles at every shape tried (n = 2048 x 64: 10.4 vs 11.1 ms;
+// n = 1024 x 128: 3.6 vs 3.75 ms): the launches of the late block columns have few tiles per SM, and the finer tiles fill the
+// last round.  CCGP_BIG_ROWS = 128 forces the tall tiles.
+inline int big_update_rows(int rows, int nb, int num_sm) {
+    const char* e = getenv("CCGP_BIG_ROWS");
+    if (e && *e) return atoi(e) == 64 ? 64 : 128;
+    (void)rows; (void)nb; (void)num_sm;
+    return 64;
+}
+template <bool TRSM>
+inline void big_update_launch(const BigArgs& G, int k, int chlo, int chhi, int rows, int nb, int num_sm, cudaStream_t st) {
+    if (big_update_rows(rows, nb, num_sm) == 64)
+        big_update_kernel<TRSM, 64><<<dim3((rows + 63) / 64, nb), 256, 2 * bu_stage<64>() * 8, st>>>(G, k, chlo, chhi);
+    else
+        big_update_kernel<TRSM, 128><<<dim3((rows + 127) / 128, nb), 256, 2 * bu_stage<128>() * 8, st>>>(G, k, chlo, chhi);
 }
 
 __global__ void __launch_bounds__(256) big_finish_kernel(BigArgs G, int64_t b0, double sigma2, int mean_mode, double tau,
@@ -485,7 +529,8 @@ inline int bigchol_nll_batch(BigCholWorkspace& ws, cudaStream_t stream, int num_
                              const int32_t* d_idx = nullptr, int64_t ldi = 0, int64_t ldx = 0) {
 #define BIGCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
         snprintf(err, errlen, "bigchol %s: %s", #call, cudaGetErrorString(e_)); return -2; } } while (0)
-    const int ncp = (n + 63) / 64 * 64, nrp = ncp + 64, T = ncp / 64;
+    const bool right_looking = getenv("CCGP_BIG_RIGHT") && atoi(getenv("CCGP_BIG_RIGHT"));   // the old schedule, for A/B runs
+    const int ncp = (n + 63) / 64 * 64, nrp = ncp + (right_looking ? 64 : 8), T = ncp / 64;
     const size_t per = (size_t)nrp * ncp * 8;
     size_t freeb = 0, totalb = 0;
     BIGCK(cudaMemGetInfo(&freeb, &totalb));
@@ -503,8 +548,10 @@ inline int bigchol_nll_batch(BigCholWorkspace& ws, cudaStream_t stream, int num_
         ws.cap = chunk;
     }
     BIGCK(cudaFuncSetAttribute(big_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 64 * 72 * 8));
-    BIGCK(cudaFuncSetAttribute(big_update_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * BU_STAGE * 8));
-    BIGCK(cudaFuncSetAttribute(big_update_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * BU_STAGE * 8));
+    BIGCK(cudaFuncSetAttribute(big_update_kernel<false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * bu_stage<128>() * 8));
+    BIGCK(cudaFuncSetAttribute(big_update_kernel<true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * bu_stage<128>() * 8));
+    BIGCK(cudaFuncSetAttribute(big_update_kernel<false, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * bu_stage<64>() * 8));
+    BIGCK(cudaFuncSetAttribute(big_update_kernel<true, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * bu_stage<64>() * 8));
     BIGCK(cudaFuncSetAttribute(big_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 64 * 65 * 8));
     FactorArgs F;
     memset(&F, 0, sizeof(F));
@@ -521,7 +568,6 @@ inline int bigchol_nll_batch(BigCholWorkspace& ws, cudaStream_t stream, int num_
         big_params_kernel<<<(nb + 127) / 128, 128, 0, stream>>>(F, b0, nb, ws.prm, ws.logdet, ws.bad);
         big_build_kernel<<<dim3(T, T + 1, nb), 256, 0, stream>>>(G);
         *launches += 2;
-        const bool right_looking = getenv("CCGP_BIG_RIGHT") && atoi(getenv("CCGP_BIG_RIGHT"));   // the old schedule, for A/B runs
         // Lookahead (left-looking): column k's update = panels 0..k-1.  Everything but the last panel only needs columns
         // <= k-2, so it is launched as soon as column k-2 is final and overlaps the short serial kernels of column k-1
         // (last-panel update, 64x64 factor + inverse on nb CTAs, solve).  Those run on a HIGH-PRIORITY internal stream so that
@@ -547,23 +593,22 @@ inline int bigchol_nll_batch(BigCholWorkspace& ws, cudaStream_t stream, int num_
         }
         for (int k = 0; k < T; ++k) {
             if (!right_looking && k > 0) {
-                const int nrt = (nrp - k * 64 + 127) / 128;
                 const bool split = lookahead && k >= 2;
                 if (split) BIGCK(cudaStreamWaitEvent(crit, ws.ev_side[k & 1], 0));     // panels 0..k-2 are in (caller's stream)
-                big_update_kernel<false><<<dim3(nrt, nb), 256, 2 * BU_STAGE * 8, crit>>>(G, k, split ? 2 * (k - 1) : 0, 2 * k);
+                big_update_launch<false>(G, k, split ? 2 * (k - 1) : 0, 2 * k, nrp - k * 64, nb, num_sm, crit);
                 *launches += 1;
             }
             if (potrf_old) big_potrf_kernel<<<nb, 256, 0, crit>>>(G, k);
             else big_potrf_mma_kernel<<<nb, 256, 0, crit>>>(G, k);
-            const int rt = (nrp - (k + 1) * 64) / 64;           // row tiles below the diagonal block
+            const int rows_below = nrp - (k + 1) * 64;          // rows below the diagonal block (>= 8: the extra rows)
+            const int rt = rows_below / 64;                     // (64-row tiles of the right-looking schedule)
             if (rt > 0 && right_looking) big_trsm_kernel<<<dim3(rt, nb), 64, 2 * 64 * 65 * 8, crit>>>(G, k);
-            else if (rt > 0) big_update_kernel<true><<<dim3((rt * 64 + 127) / 128, nb), 256, 2 * BU_STAGE * 8, crit>>>(G, k, 0, 2);
+            else if (rows_below > 0) big_update_launch<true>(G, k, 0, 2, rows_below, nb, num_sm, crit);
             *launches += 2;
             if (lookahead && k + 2 < T) {                       // column k is final: panels 0..k of column k+2, the bulk
                 BIGCK(cudaEventRecord(ws.ev_main, crit));
                 BIGCK(cudaStreamWaitEvent(stream, ws.ev_main, 0));
-                const int nrt2 = (nrp - (k + 2) * 64 + 127) / 128;
-                big_update_kernel<false><<<dim3(nrt2, nb), 256, 2 * BU_STAGE * 8, stream>>>(G, k + 2, 0, 2 * (k + 1));
+                big_update_launch<false>(G, k + 2, 0, 2 * (k + 1), nrp - (k + 2) * 64, nb, num_sm, stream);
                 BIGCK(cudaEventRecord(ws.ev_side[k & 1], stream));              // (k + 2) & 1: waited on at step k + 2, re-recorded after that wait
                 *launches += 1;
             }
