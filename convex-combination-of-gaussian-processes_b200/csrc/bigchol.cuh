@@ -562,30 +562,29 @@ inline int bigchol_nll_batch(BigCholWorkspace& ws, cudaStream_t stream, int num_
     G.A = ws.A; G.n = n; G.d = d; G.ncp = ncp; G.nrp = nrp; G.stride = (int64_t)nrp * ncp;
     G.X = d_X; G.y = d_y; G.prm = ws.prm; G.logdet = ws.logdet; G.bad = ws.bad; G.linv = ws.linv;
     G.idx = d_idx; G.ldi = ldi; G.ldx = d_idx ? ldx : n; G.b0 = 0;
-    for (int64_t b0 = 0; b0 < B; b0 += chunk) {
-        const int nb = (int)std::min<int64_t>(chunk, B - b0);
+    const bool potrf_old = getenv("CCGP_BIG_POTRF_OLD") && atoi(getenv("CCGP_BIG_POTRF_OLD"));
+    const char* la_env = getenv("CCGP_BIG_LOOKAHEAD");
+    // Lookahead (left-looking): column k's update = panels 0..k-1.  Everything but the last panel only needs columns
+    // <= k-2, so it is launched as soon as column k-2 is final and overlaps the short serial kernels of column k-1
+    // (last-panel update, 64x64 factor + inverse on nb CTAs, solve).  Those run on a HIGH-PRIORITY internal stream so that
+    // their few CTAs take the first slots the bulk update's CTAs free; the bulk stays on the caller's stream.
+    // On from 24 block columns (n = 1024 x 128 got slower with it), CCGP_BIG_LOOKAHEAD = 0 / 1 forces it.
+    const bool lookahead = !right_looking && ((la_env && *la_env) ? atoi(la_env) != 0 : T >= 24);
+    if (lookahead && !ws.side) {
+        int lo = 0, hi = 0;
+        BIGCK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        BIGCK(cudaStreamCreateWithPriority(&ws.side, cudaStreamNonBlocking, hi));
+        BIGCK(cudaEventCreateWithFlags(&ws.ev_main, cudaEventDisableTiming));
+        BIGCK(cudaEventCreateWithFlags(&ws.ev_side[0], cudaEventDisableTiming));
+        BIGCK(cudaEventCreateWithFlags(&ws.ev_side[1], cudaEventDisableTiming));
+    }
+    // every launch of one chunk of candidates (b0 .. b0 + nb), in stream order; returns the number of launches or < 0
+    auto enqueue_chunk = [&](int64_t b0, int nb) -> int {
+        int nl = 0;
         G.b0 = b0;
         big_params_kernel<<<(nb + 127) / 128, 128, 0, stream>>>(F, b0, nb, ws.prm, ws.logdet, ws.bad);
         big_build_kernel<<<dim3(T, T + 1, nb), 256, 0, stream>>>(G);
-        *launches += 2;
-        // Lookahead (left-looking): column k's update = panels 0..k-1.  Everything but the last panel only needs columns
-        // <= k-2, so it is launched as soon as column k-2 is final and overlaps the short serial kernels of column k-1
-        // (last-panel update, 64x64 factor + inverse on nb CTAs, solve).  Those run on a HIGH-PRIORITY internal stream so that
-        // their few CTAs take the first slots the bulk update's CTAs free (the bulk kernel alone fills every SM's shared
-        // memory); the bulk stays on the caller's stream.
-        // Measured (tools/bench_large_n.py): n = 2048 x 64 candidates 12.9 -> 12.4 ms, n = 1024 x 128 4.7 -> 5.2 ms (the extra
-        // launches cost more than the short chain they hide): on from 24 block columns, CCGP_BIG_LOOKAHEAD = 0 / 1 forces it.
-        const bool potrf_old = getenv("CCGP_BIG_POTRF_OLD") && atoi(getenv("CCGP_BIG_POTRF_OLD"));
-        const char* la_env = getenv("CCGP_BIG_LOOKAHEAD");
-        const bool lookahead = !right_looking && ((la_env && *la_env) ? atoi(la_env) != 0 : T >= 24);
-        if (lookahead && !ws.side) {
-            int lo = 0, hi = 0;
-            BIGCK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-            BIGCK(cudaStreamCreateWithPriority(&ws.side, cudaStreamNonBlocking, hi));
-            BIGCK(cudaEventCreateWithFlags(&ws.ev_main, cudaEventDisableTiming));
-            BIGCK(cudaEventCreateWithFlags(&ws.ev_side[0], cudaEventDisableTiming));
-            BIGCK(cudaEventCreateWithFlags(&ws.ev_side[1], cudaEventDisableTiming));
-        }
+        nl += 2;
         cudaStream_t crit = lookahead ? ws.side : stream;       // the serial chain of every block column
         if (lookahead) {                                        // the chain starts after the build
             BIGCK(cudaEventRecord(ws.ev_side[0], stream));
@@ -596,7 +595,7 @@ inline int bigchol_nll_batch(BigCholWorkspace& ws, cudaStream_t stream, int num_
                 const bool split = lookahead && k >= 2;
                 if (split) BIGCK(cudaStreamWaitEvent(crit, ws.ev_side[k & 1], 0));     // panels 0..k-2 are in (caller's stream)
                 big_update_launch<false>(G, k, split ? 2 * (k - 1) : 0, 2 * k, nrp - k * 64, nb, num_sm, crit);
-                *launches += 1;
+                nl += 1;
             }
             if (potrf_old) big_potrf_kernel<<<nb, 256, 0, crit>>>(G, k);
             else big_potrf_mma_kernel<<<nb, 256, 0, crit>>>(G, k);
@@ -604,20 +603,20 @@ inline int bigchol_nll_batch(BigCholWorkspace& ws, cudaStream_t stream, int num_
             const int rt = rows_below / 64;                     // (64-row tiles of the right-looking schedule)
             if (rt > 0 && right_looking) big_trsm_kernel<<<dim3(rt, nb), 64, 2 * 64 * 65 * 8, crit>>>(G, k);
             else if (rows_below > 0) big_update_launch<true>(G, k, 0, 2, rows_below, nb, num_sm, crit);
-            *launches += 2;
+            nl += 2;
             if (lookahead && k + 2 < T) {                       // column k is final: panels 0..k of column k+2, the bulk
                 BIGCK(cudaEventRecord(ws.ev_main, crit));
                 BIGCK(cudaStreamWaitEvent(stream, ws.ev_main, 0));
                 big_update_launch<false>(G, k + 2, 0, 2 * (k + 1), nrp - (k + 2) * 64, nb, num_sm, stream);
                 BIGCK(cudaEventRecord(ws.ev_side[k & 1], stream));              // (k + 2) & 1: waited on at step k + 2, re-recorded after that wait
-                *launches += 1;
+                nl += 1;
             }
             const int ct = T - (k + 1);                         // real block columns still to update
             if (right_looking && ct > 0) {
                 // tiles (ti, tj) with tj < ct, ti in [tj, rt): sum_{tj<ct} (rt - tj)
                 const int ntiles = ct * rt - ct * (ct - 1) / 2;
                 big_syrk_kernel<<<dim3(ntiles, nb), 128, 2 * 64 * 72 * 8, stream>>>(G, k, rt);
-                *launches += 1;
+                nl += 1;
             }
         }
         if (lookahead) {                                        // back on the caller's stream
@@ -626,7 +625,53 @@ inline int bigchol_nll_batch(BigCholWorkspace& ws, cudaStream_t stream, int num_
         }
         if (d_idx) big_logdet_out_kernel<<<(nb + 127) / 128, 128, 0, stream>>>(G, nb, d_nll, d_status);
         else big_finish_kernel<<<nb, 256, 0, stream>>>(G, b0, sigma2, mean_mode, tau, d_nll, d_beta, d_status);
-        *launches += 1;
+        nl += 1;
+        return nl;
+    };
+    // A batch is ~130 short launches on two streams: a caller that repeats the same call (same buffers, same sizes -- the
+    // host-pointer API always does, it works out of the context's workspace) gets the schedule as a CUDA graph from the second
+    // identical call on: one cudaGraphLaunch instead of ~130 launches + 2 x 60 event operations, so a busy host no longer
+    // starves the GPU between the 75 us kernels.  CCGP_BIG_GRAPH = 0 turns it off.
+    BigGraphKey key;
+    memset(&key, 0, sizeof(key));
+    key.A = ws.A; key.prm = ws.prm; key.linv = ws.linv; key.X = d_X; key.y = d_y; key.cand = d_cand; key.nll = d_nll; key.beta = d_beta;
+    key.status = d_status; key.idx = d_idx; key.B = B; key.ldc = ldc; key.ldi = ldi; key.ldx = ldx; key.sigma2 = sigma2; key.tau = tau;
+    key.n = n; key.d = d; key.family = family; key.scale = scale; key.mean_mode = mean_mode; key.nrp = nrp;
+    key.flags = (right_looking ? 1 : 0) | (lookahead ? 2 : 0) | (potrf_old ? 4 : 0) | (big_update_rows(0, 0, 0) == 64 ? 8 : 0);
+    key.stream = stream;
+    const char* g_env = getenv("CCGP_BIG_GRAPH");
+    const bool graphs = !(g_env && *g_env && atoi(g_env) == 0) && B <= chunk && stream != nullptr;
+    if (graphs && ws.gexec && memcmp(&key, &ws.gkey, sizeof(key)) == 0) {
+        BIGCK(cudaGraphLaunch(ws.gexec, stream));
+        *launches += ws.glaunches;
+        return 0;
+    }
+    if (graphs && ws.have_last && memcmp(&key, &ws.last_key, sizeof(key)) == 0) {      // second identical call: capture, keep, launch
+        cudaGraph_t graph = nullptr;
+        if (cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            const int nl = enqueue_chunk(0, (int)B);
+            const cudaError_t ee = cudaStreamEndCapture(stream, &graph);
+            cudaGraphExec_t ge = nullptr;
+            if (nl > 0 && ee == cudaSuccess && graph && cudaGraphInstantiate(&ge, graph, 0) == cudaSuccess) {
+                if (ws.gexec) cudaGraphExecDestroy(ws.gexec);
+                ws.gexec = ge; ws.gkey = key; ws.glaunches = nl;
+                cudaGraphDestroy(graph);
+                BIGCK(cudaGraphLaunch(ws.gexec, stream));
+                *launches += nl;
+                return 0;
+            }
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();                                 // capture failed: fall through to the plain launches
+        } else {
+            cudaGetLastError();
+        }
+    }
+    ws.last_key = key; ws.have_last = true;
+    for (int64_t b0 = 0; b0 < B; b0 += chunk) {
+        const int nb = (int)std::min<int64_t>(chunk, B - b0);
+        const int nl = enqueue_chunk(b0, nb);
+        if (nl < 0) return nl;
+        *launches += nl;
         BIGCK(cudaGetLastError());
     }
 #undef BIGCK

@@ -41,13 +41,14 @@ print("per-rep ms (one call per event pair; includes the host's enqueue time):",
 # nine batches queued back to back, as bench.py's large_n block does: the host runs ahead of the GPU
 tq = []
 for _ in range(3):
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(9):
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(10)]
+    evs[0].record(stream)
+    for i in range(9):
         eng.nll_batch_dev(cand, GAUSS_ANISO_LAMBDA, 1.0, out_nll=out[0], out_beta=out[1], out_status=out[2])
-    e1.record(stream)
+        evs[i + 1].record(stream)
     torch.cuda.synchronize()
-    tq.append(e0.elapsed_time(e1) / 9)
+    tq.append(evs[0].elapsed_time(evs[9]) / 9)
+    print("   queued batches, ms each:", " ".join("%.2f" % evs[i].elapsed_time(evs[i + 1]) for i in range(9)))
 print("queued x9, ms per batch:", " ".join("%.2f" % t for t in tq))
 reps += 27
 ms = min(tq)
