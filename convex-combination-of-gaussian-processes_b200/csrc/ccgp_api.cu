@@ -694,9 +694,26 @@ static int predict_mma_launch(ccgp_ctx* ctx, PredictArgs& P, int* launched) {
     if (nb < 1) return 0;
     const int64_t slots = (int64_t)nb * ctx->num_sm;
     P.t_chunks = 1;
-    if (P.fac_mode == 0 && A.W * 2 <= slots && P.T >= 128 && !env_int("CCGP_PREDICT_NOSPLIT", 0)) {
-        // few posterior rows, many sites (the plug-in / posterior-mean surface over a grid): factor the rows into a scratch
-        // buffer, then run the site phase with the sites of a row split over the idle CTAs -- same values, two launches
+    // Site chunks per row.  A CTA takes one (row, chunk) item at a time, so the launch lasts ceil(items / slots) rounds of
+    // 1 / chunks of a row's site phase each: with fewer rows than resident CTAs the idle CTAs take shares of the sites, and with
+    // a few rounds' worth of rows (S = 1000 on 296 slots: 4 rounds, the last 38 % full) finer items fill the last round.
+    // 64 sites = one pass of the four warps is the smallest useful share.
+    // Cost model in units of one pass (16 sites per warp through the NJ column steps): an item of c chunks per row takes
+    // ceil(groups / c / 4 warps) passes plus ~0.4 for loading the factor; measured against it: n = 100, S = 1000, T = 625
+    // 591 -> 531 us with c = 2; n = 50, T = 150 (10 groups) is better left whole.
+    const int64_t ngrp = (P.T + 8 * PM_G - 1) / (8 * PM_G);
+    auto cost = [&](int64_t c) {
+        const int64_t per_item = ((ngrp + c - 1) / c + PM_NW - 1) / PM_NW;
+        return (double)((A.W * c + slots - 1) / slots) * ((double)per_item + 0.4);
+    };
+    int64_t best_c = 1;
+    for (int64_t c = 2; c <= std::min<int64_t>((ngrp + PM_NW - 1) / PM_NW, 64); ++c)
+        if (cost(c) < 0.95 * cost(best_c)) best_c = c;
+    if (P.fac_mode == 0 && !env_int("CCGP_PREDICT_NOSPLIT", 0) &&
+        ((A.W * 2 <= slots && P.T >= 128) || (P.T >= 256 && cost(best_c) + 1.0 <= 0.9 * cost(1)))) {
+        // the direct call takes the same route when it pays for a second launch and the trip of the factors through HBM:
+        // few rows and many sites (the plug-in / posterior-mean surface over a grid), or a badly filled last round --
+        // factor the rows into a scratch buffer, then the site phase over (row, chunk) items; same values
         const int64_t fac_ld = (int64_t)l.total + (int64_t)l.NJ * 64 + 2;
         const size_t need = (size_t)A.W * fac_ld * 8;
         if (need > ctx->fac_scratch_bytes) {
@@ -706,17 +723,12 @@ static int predict_mma_launch(ccgp_ctx* ctx, PredictArgs& P, int* launched) {
         }
         PredictArgs Q = P;
         Q.fac = ctx->fac_scratch; Q.fac_ld = fac_ld; Q.fac_mode = 1; Q.T = 0;
-        fn<<<(unsigned)A.W, PM_NW * 32, smem, ctx->stream>>>(Q);
+        fn<<<(unsigned)std::min<int64_t>(A.W, slots), PM_NW * 32, smem, ctx->stream>>>(Q);
         CK(cudaGetLastError());
         ctx->launches++;
         P.fac = ctx->fac_scratch; P.fac_ld = fac_ld; P.fac_mode = 2;
     }
-    if (P.fac_mode == 2 && A.W < slots) {
-        // stored factors, fewer rows than resident CTAs: the sites of a row are split over several CTAs (64 sites = one pass
-        // of the four warps is the smallest useful share)
-        const int64_t passes = (P.T + 63) / 64;
-        P.t_chunks = (int)std::max<int64_t>(1, std::min<int64_t>(passes, slots / A.W));
-    }
+    if (P.fac_mode == 2) P.t_chunks = (int)best_c;
     const int64_t grid = std::min<int64_t>(A.W * P.t_chunks, slots);
     fn<<<(unsigned)grid, PM_NW * 32, smem, ctx->stream>>>(P);
     CK(cudaGetLastError());
