@@ -710,9 +710,10 @@ static int predict_mma_launch(ccgp_ctx* ctx, PredictArgs& P, int* launched) {
     for (int64_t c = 2; c <= std::min<int64_t>((ngrp + PM_NW - 1) / PM_NW, 64); ++c)
         if (cost(c) < 0.95 * cost(best_c)) best_c = c;
     if (P.fac_mode == 0 && !env_int("CCGP_PREDICT_NOSPLIT", 0) &&
-        ((A.W * 2 <= slots && P.T >= 128) || (P.T >= 256 && cost(best_c) + 1.0 <= 0.9 * cost(1)))) {
+        ((A.W * 2 <= slots && P.T >= 128) || (P.T >= 256 && l.NJ >= 8 && cost(best_c) + 1.0 <= 0.95 * cost(1)))) {
         // the direct call takes the same route when it pays for a second launch and the trip of the factors through HBM:
-        // few rows and many sites (the plug-in / posterior-mean surface over a grid), or a badly filled last round --
+        // few rows and many sites (the plug-in / posterior-mean surface over a grid), or a badly filled last round on designs
+        // large enough for a pass to outweigh a launch (n = 14: 93 -> 108 us, n = 100: 663 -> 632 us) --
         // factor the rows into a scratch buffer, then the site phase over (row, chunk) items; same values
         const int64_t fac_ld = (int64_t)l.total + (int64_t)l.NJ * 64 + 2;
         const size_t need = (size_t)A.W * fac_ld * 8;

@@ -382,6 +382,42 @@ def test_large_n_vs_oracle(engine, n):
         assert rel_err(beta[b], m["beta"]) < 1e-9
 
 
+def test_large_n_repeated_call_replays_graph(engine):
+    """The blocked path replays its schedule (~5 launches per block column on two streams) as a CUDA graph from the second
+    identical call on (bigchol_nll_batch): values, status and the launch count per call must not change, new parameter
+    VALUES in the same buffers go through the same graph, and CCGP_BIG_GRAPH=0 / the old right-looking schedule agree."""
+    n = 460
+    X = workloads.synthetic_pool(n, seed=11)
+    rng = np.random.default_rng(12)
+    y = np.sin(3 * X[:, 0]) * np.cos(2 * X[:, 1]) + 0.05 * rng.normal(size=n)
+    h2 = 4.0 / n
+    nat = np.column_stack([rng.uniform(0.2, 0.8, 6), rng.uniform(1.2, 2.5, 6) / h2, rng.uniform(1.2, 2.5, 6) / h2, rng.uniform(0.5, 2, 6)])
+    engine.set_design(X, y)
+    runs, counts = [], []
+    for rep in range(4):                                   # plain, capture + launch, replay, replay
+        l0 = engine.launch_count
+        runs.append(engine.nll_batch(nat, GAUSS_ANISO_LAMBDA, 1.3))
+        counts.append(engine.launch_count - l0)
+    assert len(set(counts)) == 1 and counts[0] > 20
+    for r in runs[1:]:
+        assert np.array_equal(r[0], runs[0][0]) and np.array_equal(r[1], runs[0][1]) and np.array_equal(r[2], runs[0][2])
+    nat2 = nat[::-1].copy()                                # same shapes and buffers, other values: still the graph
+    a = engine.nll_batch(nat2, GAUSS_ANISO_LAMBDA, 1.3)
+    assert np.array_equal(a[0], runs[0][0][::-1]) and np.array_equal(a[1], runs[0][1][::-1])
+    for env in ({"CCGP_BIG_GRAPH": "0"}, {"CCGP_BIG_RIGHT": "1"}, {"CCGP_BIG_ROWS": "128"}, {"CCGP_BIG_LOOKAHEAD": "1"}):
+        os.environ.update(env)
+        try:
+            for rep in range(3):
+                b = engine.nll_batch(nat, GAUSS_ANISO_LAMBDA, 1.3)
+        finally:
+            for k in env:
+                os.environ.pop(k, None)
+        assert np.array_equal(b[2], runs[0][2])
+        assert rel_err(b[0], runs[0][0]).max() < 1e-11 and rel_err(b[1], runs[0][1]).max() < 1e-9, env
+    o = orc.loglik_minimal(X, y, 1.3, orc.FAMILY_ANISO_LAMBDA, nat[0])
+    assert rel_err(-runs[0][0][0], o["loglik"]) < TOL
+
+
 # ---------------------------------------------------------------- 1-D families (SURVEY 8a row a16)
 @pytest.mark.parametrize("tag,family,ofam", [("d1mm", ccgp_b200.MATERN1D, orc.FAMILY_MATERN1D),
                                              ("d1ms", ccgp_b200.MATERN_SPLINE1D, orc.FAMILY_MATERN_SPLINE1D)])
