@@ -15,7 +15,13 @@
 // exchanged through a per-warp shared buffer for S, and the 8x8 factorisation runs on
 // width-8 shuffles.  Deterministic: one fixed evaluation order per (candidate, row).
 #pragma once
+#include <algorithm>
+#include <cstdlib>
 #include "factor_engine.cuh"
+
+#ifndef CCGP_ME_BALANCED_DEFAULT
+#define CCGP_ME_BALANCED_DEFAULT false
+#endif
 
 namespace ccgp {
 
@@ -28,6 +34,9 @@ struct MeArgs {
     int64_t C, P;
     int64_t chunk;         // candidates per work item
     int64_t nchunks;       // ceil(candidates per parameter row / chunk)
+    int64_t ppr;           // > 0: balanced schedule -- passes (16 candidates) per parameter row; CTA b takes the
+                           // contiguous range [T b / grid, T (b+1) / grid) of the P * ppr passes and factors R.old
+                           // once per row it touches (same values: the per-(candidate, row) order is fixed)
     int64_t group;         // 0: every design x every parameter row; G > 0: designs [qG, (q+1)G) belong to row q (C = P G)
     int stencil;           // S > 0: D_new holds C/S base designs; design c is base c/S with the central-difference
                            // perturbation (c%S): 0 none, 1+2i: coordinate i + h, 2+2i: coordinate i - h (clipped to [lo, hi])
@@ -64,9 +73,12 @@ __global__ void __launch_bounds__(128) me_schur_kernel(const MeArgs M) {
     }
     etab[tid] = CCGP_EXP2_TAB[tid];
 
-    const int64_t nitems = M.P * M.nchunks;
-    for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
-        const int64_t q = item / M.nchunks, ch = item - q * M.nchunks;
+    const bool balanced = M.ppr > 0;
+    const int64_t npass = M.P * M.ppr;
+    const int64_t ps0 = balanced ? npass * blockIdx.x / gridDim.x : 0, ps1 = balanced ? npass * (blockIdx.x + 1) / gridDim.x : 0;
+    const int64_t nitems = balanced ? (ps1 > ps0 ? (ps1 - 1) / M.ppr + 1 : 0) : M.P * M.nchunks;
+    for (int64_t item = balanced ? ps0 / M.ppr : blockIdx.x; item < nitems; item += balanced ? 1 : gridDim.x) {
+        const int64_t q = balanced ? item : item / M.nchunks, ch = balanced ? 0 : item - q * M.nchunks;
         __syncthreads();
         if (tid == 0) {
             const double p = M.params[q], t1 = M.params[q + M.ldq], t2 = M.params[q + 2 * M.ldq];
@@ -113,7 +125,11 @@ __global__ void __launch_bounds__(128) me_schur_kernel(const MeArgs M) {
 
         // ---- candidates of this chunk: 16 per pass (4 warps x 4 groups) -----------------------
         const int64_t c_beg = M.group ? q * M.group : 0, c_end = M.group ? c_beg + M.group : M.C;
-        const int64_t c_lo = c_beg + ch * M.chunk, c_hi = min(c_end, c_lo + M.chunk);
+        int64_t c_lo = c_beg + ch * M.chunk, c_hi = min(c_end, c_lo + M.chunk);
+        if (balanced) {                                   // the passes of row q inside [ps0, ps1)
+            c_lo = c_beg + (max(ps0, q * M.ppr) - q * M.ppr) * 16;
+            c_hi = min(c_end, c_beg + (min(ps1, (q + 1) * M.ppr) - q * M.ppr) * 16);
+        }
         for (int64_t c0 = c_lo; c0 < c_hi; c0 += 16) {
             const int64_t c = c0 + warp * 4 + grp;
             const bool valid = c < c_hi;
@@ -222,18 +238,28 @@ inline int me_fast_launch(cudaStream_t stream, int num_sm, const double* d_D_old
     M.nchunks = (Cq + chunk - 1) / chunk;
     M.negdet = d_negdet; M.logdet = d_logdet; M.status = d_status;
     const int64_t items = P * M.nchunks;
-    const int grid = (int)std::min<int64_t>(items, (int64_t)num_sm * 8);
+    int grid = (int)std::min<int64_t>(items, (int64_t)num_sm * 8);
+    // Balanced schedule (CCGP_ME_BALANCED, see MeArgs::ppr): one CTA per resident slot, equal pass counts.
+    // The chunked grid above is 8 CTAs per SM against 5 resident (86 registers): the second wave runs 60 % full.
+    const char* ev = getenv("CCGP_ME_BALANCED");
+    const bool balanced = ev ? atoi(ev) != 0 : CCGP_ME_BALANCED_DEFAULT;
+    const char* ec = getenv("CCGP_ME_CTAS");               // CTAs per SM of the balanced grid (0: the occupancy query)
+    const int ctas_env = ec ? atoi(ec) : 0;
+    M.ppr = balanced ? (Cq + 15) / 16 : 0;
     // 14 = the reference's initial design ([M]:980); d = 2 in the shipped script
-#define CCGP_ME_LAUNCH(NO) do { if (stencil) { if (d <= 2) me_schur_kernel<NO, 2, true><<<grid, 128, 0, stream>>>(M); \
-                                               else me_schur_kernel<NO, 4, true><<<grid, 128, 0, stream>>>(M); } \
-                                else if (d <= 2) me_schur_kernel<NO, 2, false><<<grid, 128, 0, stream>>>(M); \
-                                else me_schur_kernel<NO, 4, false><<<grid, 128, 0, stream>>>(M); } while (0)
+#define CCGP_ME_GO(NO, DMV, ST) do { if (balanced) { int occ = ctas_env; \
+            if (occ <= 0 && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, me_schur_kernel<NO, DMV, ST>, 128, 0) != cudaSuccess) occ = 4; \
+            grid = (int)std::min<int64_t>(P * M.ppr, (int64_t)num_sm * std::max(occ, 1)); } \
+        me_schur_kernel<NO, DMV, ST><<<grid, 128, 0, stream>>>(M); } while (0)
+#define CCGP_ME_LAUNCH(NO) do { if (stencil) { if (d <= 2) CCGP_ME_GO(NO, 2, true); else CCGP_ME_GO(NO, 4, true); } \
+                                else if (d <= 2) CCGP_ME_GO(NO, 2, false); else CCGP_ME_GO(NO, 4, false); } while (0)
     if (n_old <= 8) CCGP_ME_LAUNCH(8);
     else if (n_old <= 14) CCGP_ME_LAUNCH(14);
     else if (n_old <= 16) CCGP_ME_LAUNCH(16);
     else if (n_old <= 24) CCGP_ME_LAUNCH(24);
     else CCGP_ME_LAUNCH(32);
 #undef CCGP_ME_LAUNCH
+#undef CCGP_ME_GO
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { snprintf(err, errlen, "me_schur_kernel launch: %s", cudaGetErrorString(e)); return -2; }
     return 0;

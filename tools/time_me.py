@@ -26,6 +26,34 @@ d_new = torch.from_numpy(np.stack([p.flatten(order="F") for p in pool])).to(dev)
 d_par = torch.from_numpy(np.asfortranarray(params).T.copy()).to(dev)
 out = torch.empty(C * P, dtype=torch.float64, device=dev)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+
+def run_once():
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    flush.zero_()
+    e0.record(stream)
+    eng.me_schur_batch_dev(d_old, 14, 2, d_new, 7, C, d_par, P, out)
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    return e0.elapsed_time(e1)
+
+
+if len(sys.argv) > 3 and sys.argv[3] == "ab":
+    # A/B of the chunked schedule against the balanced one (CCGP_ME_BALANCED, read at every launch): same bits, time
+    os.environ["CCGP_ME_BALANCED"] = "0"
+    t_old = min(run_once() for _ in range(reps + 1))
+    ref = out.clone()
+    print("chunked schedule (8 CTAs/SM grid): %.4f ms  %.3f G dets/s" % (t_old, C * P / t_old / 1e6))
+    os.environ["CCGP_ME_BALANCED"] = "1"
+    for ctas in (0, 3, 4, 5, 6, 8):
+        os.environ["CCGP_ME_CTAS"] = str(ctas)
+        out.zero_()
+        t_new = min(run_once() for _ in range(reps + 1))
+        same = bool(torch.equal(out.view(torch.int64), ref.view(torch.int64)))
+        print("balanced schedule, CTAs/SM %s: %.4f ms  %.3f G dets/s  bit-identical to chunked: %s"
+              % (ctas or "occupancy query", t_new, C * P / t_new / 1e6, same))
+    sys.exit(0)
+
 ts = []
 for it in range(reps):
     flush.zero_()
