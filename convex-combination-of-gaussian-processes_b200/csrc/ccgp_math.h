@@ -153,6 +153,28 @@ __device__ __forceinline__ double dexp_neg_tab_dev(double s, const double* T) {
     const double v = fma(Tv, p, Tv);
     return __hiloint2double(__double2hiint(v) + (e << 20), __double2loint(v));
 }
+// the same with the clamp s <= ~700 done on the high word (one integer min instead of DSETP + two selects): for
+// s >= 0 the order of doubles is the order of their high words; identical bits for s < 700, exp(-700.0005) ~ 1e-304
+// at most beyond; negative and NaN arguments behave as with fmin (negative kept, NaN -> the clamp value).
+// s <= 700.0005 keeps k >= -129267, so the exponent step k >> 7 >= -1010 needs no guard of its own.
+// STRIDE: the table is replicated STRIDE times (entry j of copy c at T0[j * STRIDE + c]); the caller passes T = T0 + its
+// copy, so the lanes of a half-warp hit different banks whatever their arguments (one table, random j: ~5 extra wavefronts)
+template <int STRIDE>
+__device__ __forceinline__ double dexp_neg_tab_dev_ic(double s, const double* T) {
+    s = __hiloint2double(min(__double2hiint(s), 0x4085E000), __double2loint(s));
+    const double t = fma(-s, c_dexpt[1], c_dexpt[0]);
+    const double kf = t - c_dexpt[0];
+    double r = fma(kf, c_dexpt[2], -s);
+    r = fma(kf, c_dexpt[3], r);
+    const int k = __double2loint(t);
+    const double Tv = T[(k & 127) * STRIDE];
+    double q = fma(r, c_dexpt[4], c_dexpt[5]);
+    q = fma(q, r, c_dexpt[6]);
+    q = fma(q, r, 0.5);
+    const double p = fma(r * r, q, r);
+    const double v = fma(Tv, p, Tv);
+    return __hiloint2double(__double2hiint(v) + ((k >> 7) << 20), __double2loint(v));
+}
 #endif
 
 CCGP_HD double dexp_neg(double s) {

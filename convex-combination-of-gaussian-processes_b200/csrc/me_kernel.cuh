@@ -16,11 +16,15 @@
 // width-8 shuffles.  Deterministic: one fixed evaluation order per (candidate, row).
 #pragma once
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include "factor_engine.cuh"
 
+#ifndef CCGP_ME_SYM_DEFAULT
+#define CCGP_ME_SYM_DEFAULT true
+#endif
 #ifndef CCGP_ME_BALANCED_DEFAULT
-#define CCGP_ME_BALANCED_DEFAULT false
+#define CCGP_ME_BALANCED_DEFAULT true
 #endif
 
 namespace ccgp {
@@ -53,14 +57,24 @@ inline bool me_fast_supported(int n_old, int n_new, int d) {
 
 // NOLD: rows of the old design the kernel is unrolled for; DM: coordinates it is unrolled for (d <= DM)
 // STENCIL: designs are generated from base designs (central-difference points), see MeArgs::stencil
-template <int NOLD, int DM, bool STENCIL>
+// SYM: the symmetric block S is formed pair by pair (lane r takes the partners (r + k) mod n_new, k = 1 .. n_new/2:
+// every unordered pair once, twice for k = n_new/2 when n_new is even) and exchanged through shared memory, instead
+// of every lane forming its whole row; S(r, c) has the same bits whichever of the two lanes forms it (the squared
+// difference and the fma chain of the dot product are symmetric), so the determinants are bit-identical
+template <int NOLD, int DM, bool STENCIL, bool SYM>
 __global__ void __launch_bounds__(128) me_schur_kernel(const MeArgs M) {
+    __shared__ __align__(16) double sbuf[SYM ? 4 : 1][SYM ? 4 : 1][SYM ? 64 : 1];   // per 8-lane group: S, lower triangle
     __shared__ double Lo[NOLD * NOLD];        // L_old, row-major Lo[j*NOLD + k], k <= j
     __shared__ double rio[NOLD];              // 1 / L_old(j,j)
     __shared__ double Xo[DM * NOLD];          // D_old, Xo[k*NOLD + j]
     __shared__ double abuf[4][32][NOLD + 1];  // per warp: the solved cross rows (padded against conflicts)
     __shared__ double prm[4];                 // a, b, theta1, theta2
-    __shared__ double etab[128];              // 2^(j/128): table-driven exp (ccgp_math.h)
+    // 2^(j/128): table-driven exp (ccgp_math.h).  TREP copies, one per lane of a half-warp (dexp_neg_tab_dev_ic<STRIDE>):
+    // measured with 16 copies (profiles/r02_me_schedule_ab.txt) -- bank conflicts 41.9 M -> 14.3 M per launch, the
+    // shared-memory pipe 81 % -> 66 % of its peak, and the same 0.62 ms (the kernel is dispatch-bound again), 5 % slower at
+    // P = 60 where filling the 16 KB table per CTA shows: one copy kept
+    constexpr int TREP = 1;
+    __shared__ double etab[128 * TREP];
     __shared__ int s_bad;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_old = M.n_old, n_new = M.n_new, d = M.d;
@@ -71,7 +85,9 @@ __global__ void __launch_bounds__(128) me_schur_kernel(const MeArgs M) {
         int k = e / NOLD, j = e - k * NOLD;
         Xo[e] = (k < d && j < n_old) ? M.D_old[k * n_old + j] : 0.0;
     }
-    etab[tid] = CCGP_EXP2_TAB[tid];
+    for (int e = tid; e < 128 * TREP; e += 128) etab[e] = CCGP_EXP2_TAB[e / TREP];
+    const double* Tl = etab + (threadIdx.x & (TREP - 1));
+    if (SYM) for (int e = tid; e < 4 * 4 * 64; e += 128) (&sbuf[0][0][0])[e] = 0.0;
 
     const bool balanced = M.ppr > 0;
     const int64_t npass = M.P * M.ppr;
@@ -96,7 +112,8 @@ __global__ void __launch_bounds__(128) me_schur_kernel(const MeArgs M) {
                 double s = 0.0;
 #pragma unroll
                 for (int dd = 0; dd < DM; ++dd) { double df = Xo[dd * NOLD + j] - Xo[dd * NOLD + k]; s = fma(df, df, s); }
-                v = fma(cb, dexp_neg_tab_dev<true>(t2 * s, etab), ca * dexp_neg_tab_dev<true>(t1 * s, etab));
+                v = SYM ? fma(cb, dexp_neg_tab_dev_ic<TREP>(t2 * s, Tl), ca * dexp_neg_tab_dev_ic<TREP>(t1 * s, Tl))
+                        : fma(cb, dexp_neg_tab_dev<true>(t2 * s, etab), ca * dexp_neg_tab_dev<true>(t1 * s, etab));
             }
             Lo[e] = v;
         }
@@ -150,7 +167,10 @@ __global__ void __launch_bounds__(128) me_schur_kernel(const MeArgs M) {
                 double s = 0.0;
 #pragma unroll
                 for (int dd = 0; dd < DM; ++dd) { double df = x[dd] - Xo[dd * NOLD + j]; s = fma(df, df, s); }
-                a[j] = (j < n_old) ? fma(cb, dexp_neg_tab_dev<true>(t2 * s, etab), ca * dexp_neg_tab_dev<true>(t1 * s, etab)) : 0.0;
+                double cv;
+                if constexpr (SYM) cv = fma(cb, dexp_neg_tab_dev_ic<TREP>(t2 * s, Tl), ca * dexp_neg_tab_dev_ic<TREP>(t1 * s, Tl));
+                else cv = fma(cb, dexp_neg_tab_dev<true>(t2 * s, etab), ca * dexp_neg_tab_dev<true>(t1 * s, etab));
+                a[j] = (j < n_old) ? cv : 0.0;
             }
 #pragma unroll
             for (int j = 0; j < NOLD; ++j) {
@@ -162,35 +182,77 @@ __global__ void __launch_bounds__(128) me_schur_kernel(const MeArgs M) {
 #pragma unroll
             for (int j = 0; j < NOLD; ++j) mine[j] = a[j];
             __syncwarp();
-            // row r of S = R.new - A A' (entries c2 <= r), new-new correlations by shuffled coordinates
             double s8[8];
-#pragma unroll
-            for (int c2 = 0; c2 < 8; ++c2) {
-                double sq = 0.0;
-#pragma unroll
-                for (int dd = 0; dd < DM; ++dd) {
-                    const double xc = __shfl_sync(full, x[dd], c2, 8);
-                    const double df = x[dd] - xc;
-                    sq = fma(df, df, sq);
-                }
-                // entries c2 > r are never read and (r, r) is the unit diagonal: column n_new-1 needs no exponential
-                double v = 1.0;
-                if (c2 + 1 < n_new) v = fma(cb, dexp_neg_tab_dev<true>(t2 * sq, etab), ca * dexp_neg_tab_dev<true>(t1 * sq, etab));
-                if (c2 == r) v = 1.0;
-                const double* other = &abuf[warp][(lane & ~7) + c2][0];
-                double dot = 0.0;
-#pragma unroll
-                for (int j = 0; j < NOLD; ++j) dot = fma(a[j], other[j], dot);
-                v -= dot;
-                // rows/columns beyond n_new: identity padding
-                if (r >= n_new || c2 >= n_new) v = (c2 == r) ? 1.0 : 0.0;
-                s8[c2] = v;
-            }
-            __syncwarp();
-            // 8x8 Cholesky inside the 8-lane group; only the pivots are needed
             double dg = 1.0;
+            if constexpr (SYM) {
+                double dself = 0.0;
 #pragma unroll
-            for (int c2 = 0; c2 < 8; ++c2) if (c2 == r) dg = s8[c2];
+                for (int j = 0; j < NOLD; ++j) dself = fma(a[j], a[j], dself);
+                double* Sg = &sbuf[warp][grp][0];
+                const int K = n_new >> 1;
+#pragma unroll
+                for (int k = 1; k <= 4; ++k) {
+                    if (k <= K) {
+                        int c = r + k;
+                        if (c >= n_new) c -= n_new;
+                        if (r >= n_new) c = r;                  // padding lanes: any valid partner, nothing stored
+                        double sq = 0.0;
+#pragma unroll
+                        for (int dd = 0; dd < DM; ++dd) {
+                            const double xc = __shfl_sync(full, x[dd], c, 8);
+                            const double df = x[dd] - xc;
+                            sq = fma(df, df, sq);
+                        }
+                        double v = fma(cb, dexp_neg_tab_dev_ic<TREP>(t2 * sq, Tl), ca * dexp_neg_tab_dev_ic<TREP>(t1 * sq, Tl));
+                        const double* other = &abuf[warp][(lane & ~7) + c][0];
+                        double dot = 0.0;
+#pragma unroll
+                        for (int j = 0; j < NOLD; ++j) dot = fma(a[j], other[j], dot);
+                        v -= dot;
+                        if (r < n_new) Sg[max(r, c) * 8 + min(r, c)] = v;
+                    }
+                }
+                __syncwarp();
+                {
+                    const double2* row = reinterpret_cast<const double2*>(Sg + r * 8);
+#pragma unroll
+                    for (int c2 = 0; c2 < 8; c2 += 2) { const double2 t = row[c2 >> 1]; s8[c2] = t.x; s8[c2 + 1] = t.y; }
+                }
+                dg = 1.0 - dself;
+                if (r >= n_new) {                               // rows beyond n_new: identity padding
+                    dg = 1.0;
+#pragma unroll
+                    for (int c2 = 0; c2 < 8; ++c2) s8[c2] = 0.0;
+                }
+            } else {
+                // row r of S = R.new - A A' (entries c2 <= r), new-new correlations by shuffled coordinates
+    #pragma unroll
+                for (int c2 = 0; c2 < 8; ++c2) {
+                    double sq = 0.0;
+    #pragma unroll
+                    for (int dd = 0; dd < DM; ++dd) {
+                        const double xc = __shfl_sync(full, x[dd], c2, 8);
+                        const double df = x[dd] - xc;
+                        sq = fma(df, df, sq);
+                    }
+                    // entries c2 > r are never read and (r, r) is the unit diagonal: column n_new-1 needs no exponential
+                    double v = 1.0;
+                    if (c2 + 1 < n_new) v = fma(cb, dexp_neg_tab_dev<true>(t2 * sq, etab), ca * dexp_neg_tab_dev<true>(t1 * sq, etab));
+                    if (c2 == r) v = 1.0;
+                    const double* other = &abuf[warp][(lane & ~7) + c2][0];
+                    double dot = 0.0;
+    #pragma unroll
+                    for (int j = 0; j < NOLD; ++j) dot = fma(a[j], other[j], dot);
+                    v -= dot;
+                    // rows/columns beyond n_new: identity padding
+                    if (r >= n_new || c2 >= n_new) v = (c2 == r) ? 1.0 : 0.0;
+                    s8[c2] = v;
+                }
+                __syncwarp();
+#pragma unroll
+                for (int c2 = 0; c2 < 8; ++c2) if (c2 == r) dg = s8[c2];
+            }
+            // 8x8 Cholesky inside the 8-lane group; only the pivots are needed
             double mant = 1.0;
             int es = 0, bad = bad_old;
 #pragma unroll
@@ -239,18 +301,27 @@ inline int me_fast_launch(cudaStream_t stream, int num_sm, const double* d_D_old
     M.negdet = d_negdet; M.logdet = d_logdet; M.status = d_status;
     const int64_t items = P * M.nchunks;
     int grid = (int)std::min<int64_t>(items, (int64_t)num_sm * 8);
-    // Balanced schedule (CCGP_ME_BALANCED, see MeArgs::ppr): one CTA per resident slot, equal pass counts.
-    // The chunked grid above is 8 CTAs per SM against 5 resident (86 registers): the second wave runs 60 % full.
+    // Balanced schedule (default; CCGP_ME_BALANCED=0 restores the chunked one; see MeArgs::ppr): equal pass counts per
+    // CTA.  The chunked grid above is 8 CTAs per SM against 5 resident (94 registers): its second wave runs 60 % full.
+    // Grid: one wave (the occupancy query) until a CTA would hold more than ~48 passes, then more CTAs -- measured
+    // (profiles/r02_me_schedule_ab.txt): a staggered second wave de-phases the CTAs' exponential / solve / shuffle
+    // sections and gains another 3-4 % at P >= 1000; at P <= 250 the single wave is the fastest.
     const char* ev = getenv("CCGP_ME_BALANCED");
     const bool balanced = ev ? atoi(ev) != 0 : CCGP_ME_BALANCED_DEFAULT;
-    const char* ec = getenv("CCGP_ME_CTAS");               // CTAs per SM of the balanced grid (0: the occupancy query)
+    const char* ec = getenv("CCGP_ME_CTAS");               // CTAs per SM of the balanced grid (0: the rule above)
     const int ctas_env = ec ? atoi(ec) : 0;
     M.ppr = balanced ? (Cq + 15) / 16 : 0;
+    const char* es = getenv("CCGP_ME_SYM");                // 0: every lane forms its whole row of S (the first version)
+    const bool sym = es ? atoi(es) != 0 : CCGP_ME_SYM_DEFAULT;
     // 14 = the reference's initial design ([M]:980); d = 2 in the shipped script
-#define CCGP_ME_GO(NO, DMV, ST) do { if (balanced) { int occ = ctas_env; \
-            if (occ <= 0 && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, me_schur_kernel<NO, DMV, ST>, 128, 0) != cudaSuccess) occ = 4; \
-            grid = (int)std::min<int64_t>(P * M.ppr, (int64_t)num_sm * std::max(occ, 1)); } \
-        me_schur_kernel<NO, DMV, ST><<<grid, 128, 0, stream>>>(M); } while (0)
+#define CCGP_ME_GO(NO, DMV, ST) do { if (sym) CCGP_ME_GO2(NO, DMV, ST, true); else CCGP_ME_GO2(NO, DMV, ST, false); } while (0)
+#define CCGP_ME_GO2(NO, DMV, ST, SY) do { \
+        if (balanced) { int occ = ctas_env; \
+            if (occ <= 0 && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, me_schur_kernel<NO, DMV, ST, (SY) && ((NO) <= 24)>, 128, 0) != cudaSuccess) occ = 4; \
+            int64_t g = (int64_t)num_sm * std::max(occ, 1); \
+            if (ctas_env <= 0) g = std::max<int64_t>(g, P * M.ppr / 48); \
+            grid = (int)std::min<int64_t>(std::min<int64_t>(P * M.ppr, g), (int64_t)1 << 30); } \
+        me_schur_kernel<NO, DMV, ST, (SY) && ((NO) <= 24)><<<grid, 128, 0, stream>>>(M); } while (0)
 #define CCGP_ME_LAUNCH(NO) do { if (stencil) { if (d <= 2) CCGP_ME_GO(NO, 2, true); else CCGP_ME_GO(NO, 4, true); } \
                                 else if (d <= 2) CCGP_ME_GO(NO, 2, false); else CCGP_ME_GO(NO, 4, false); } while (0)
     if (n_old <= 8) CCGP_ME_LAUNCH(8);
@@ -260,6 +331,7 @@ inline int me_fast_launch(cudaStream_t stream, int num_sm, const double* d_D_old
     else CCGP_ME_LAUNCH(32);
 #undef CCGP_ME_LAUNCH
 #undef CCGP_ME_GO
+#undef CCGP_ME_GO2
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { snprintf(err, errlen, "me_schur_kernel launch: %s", cudaGetErrorString(e)); return -2; }
     return 0;

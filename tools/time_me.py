@@ -41,6 +41,7 @@ def run_once():
 if len(sys.argv) > 3 and sys.argv[3] == "ab":
     # A/B of the chunked schedule against the balanced one (CCGP_ME_BALANCED, read at every launch): same bits, time
     os.environ["CCGP_ME_BALANCED"] = "0"
+    os.environ["CCGP_ME_SYM"] = "0"
     t_old = min(run_once() for _ in range(reps + 1))
     ref = out.clone()
     print("chunked schedule (8 CTAs/SM grid): %.4f ms  %.3f G dets/s" % (t_old, C * P / t_old / 1e6))
@@ -52,6 +53,15 @@ if len(sys.argv) > 3 and sys.argv[3] == "ab":
         same = bool(torch.equal(out.view(torch.int64), ref.view(torch.int64)))
         print("balanced schedule, CTAs/SM %s: %.4f ms  %.3f G dets/s  bit-identical to chunked: %s"
               % (ctas or "occupancy query", t_new, C * P / t_new / 1e6, same))
+    os.environ.pop("CCGP_ME_CTAS")
+    for bal in ("0", "1"):
+        os.environ["CCGP_ME_BALANCED"] = bal
+        os.environ["CCGP_ME_SYM"] = "1"
+        out.zero_()
+        t_new = min(run_once() for _ in range(reps + 1))
+        same = bool(torch.equal(out.view(torch.int64), ref.view(torch.int64)))
+        print("pairwise S block (CCGP_ME_SYM=1), balanced %s: %.4f ms  %.3f G dets/s  bit-identical to the first version: %s"
+              % (bal, t_new, C * P / t_new / 1e6, same))
     sys.exit(0)
 
 ts = []
