@@ -391,7 +391,7 @@ def run_ours(args, rank, world, local_rank):
                            "achieved_with_exp": me_tf_exp, "frac_with_exp": me_tf_exp / (peak / 1e12),
                            "flop_per_det": ME_FLOP, "exp_per_det": ME_EXP, "exp_flop_equivalent": ME_EXP_FLOP_EQ,
                            "hbm": {"achieved_gbs": (112.0 * 1000 + 8.0 * 1000 * P) / me_kern_s / 1e9, "peak_gbs": _hbm_peak_gbs()},
-                           "traffic": None},
+                           "traffic": _me_traffic(1000 * P)},
               "cpu_baseline": me_cpu,
               "e2e": {"value": world * 1000 * P * me_steps / me_e2e_s, "unit": "dets/s",
                       "h2d_bytes_per_step": int(1000 * 14 * 8 + P * 24 + 14 * 2 * 8), "d2h_bytes_per_step": int(P * 16),
@@ -661,6 +661,15 @@ def _hbm_peak_gbs():
         return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0))
     except Exception:  # noqa: BLE001
         return 6650.0
+
+
+def _me_traffic(dets):
+    """ncu DRAM bytes of one captured ME launch (profiles/traffic.json), scaled to this launch's determinant count."""
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        return tj["me_kernel_dram_bytes_per_launch"] / tj["me_dets_per_launch"] * dets
+    except Exception:
+        return None
 
 
 def main():
