@@ -9,11 +9,13 @@
 // once per row too) each candidate needs  A = R.cross L_o^-T  (n_new forward solves),
 // S = R.new - A A'  and the product of the n_new Cholesky pivots of S.
 //
-// Mapping: a CTA takes (parameter row, chunk of candidates); it factors R.old into shared
-// memory, then every 8-lane group owns one candidate, lane r <-> new point r: the cross
-// correlations and the forward solve of row r stay in that lane's registers, rows are
-// exchanged through a per-warp shared buffer for S, and the 8x8 factorisation runs on
-// width-8 shuffles.  Deterministic: one fixed evaluation order per (candidate, row).
+// Mapping: a CTA takes a contiguous range of passes (16 candidates each) of the (parameter row, candidate) grid; it
+// factors R.old of every row it touches into shared memory, then every 8-lane group owns one candidate, lane r <-> new
+// point r: the cross correlations and the forward solve of row r stay in that lane's registers, the solved rows are
+// exchanged through a per-warp shared buffer, S is formed pair by pair (each unordered pair of new points by one lane,
+// see SYM below) and the 8x8 factorisation runs on width-8 shuffles.  Deterministic: one fixed evaluation order per
+// (candidate, row), whatever the schedule -- CCGP_ME_BALANCED=0 / CCGP_ME_SYM=0 (read at every launch) select the first
+// version's chunked schedule / row-wise S block and give the same bits (tests/test_gpu_me_variants.py).
 #pragma once
 #include <algorithm>
 #include <cstdio>
